@@ -1,0 +1,165 @@
+/*
+ * rsoccer_b200.h -- C ABI of the B200 batched robot-soccer engine
+ * (librsoccer_b200.so, built from rsoccer_b200/csrc/ for sm_100a).
+ *
+ * Drop-in boundary.  The reference crosses into native code at exactly five
+ * pybind11 methods of the third-party `robosim` module, all called from
+ * rsoccer_gym/Simulators/rsim.py.  Each entry point below names the reference
+ * call it replaces.  The ABI is plain C: opaque handle, raw pointers, sizes,
+ * `void *stream` (a cudaStream_t), int status.  No torch / pybind types.
+ *
+ *   robosim.VSS(...) / robosim.SSL(...)   rsim.py:116-124, 169-177  -> rs_create
+ *   del simulator (RSim.stop)             rsim.py:40-41             -> rs_destroy
+ *   simulator.get_field_params()          rsim.py:49-50             -> rs_field_params
+ *   simulator.reset(ball, blue, yellow)   rsim.py:36-38, 52-75      -> rs_reset
+ *   simulator.step(cmds)                  rsim.py:102, 155          -> rs_step
+ *   simulator.get_state()                 rsim.py:105, 158          -> rs_get_state
+ *
+ * and, one level up (SURVEY section 8(f) "next" rows 1-2), the whole
+ * `env.step()` of the three benchmarked task envs as ONE fused launch:
+ *
+ *   VSSEnv.step            vss/env_vss/vss_gym.py:89-91 (+ vss_gym_base.py:72-90)
+ *                                                                    -> rs_vss_env_step
+ *   SSLHWStaticDefendersEnv.step   ssl/ssl_hw_challenge/static_defenders.py:86-88
+ *   SSLContestedPossessionEnv.step ssl/ssl_hw_challenge/contested_possession.py:74-76
+ *                                                                    -> rs_ssl_env_step
+ *   env.reset()            vss_gym_base.py:92-106, vss_gym.py:194-233 -> rs_task_reset
+ *
+ * Conventions
+ *  - one rs_world = N independent matches ("envs") of one world kind on one GPU.
+ *  - every `d_*` pointer is a DEVICE pointer owned by the caller (e.g. a torch
+ *    tensor's data_ptr()); every `h_*` pointer is a HOST pointer.  The library
+ *    never retains a caller pointer past the call, except the state buffer given
+ *    to rs_bind_state, which the caller keeps alive until rs_destroy.
+ *  - calls are asynchronous on `stream` unless stated; a handle is not thread
+ *    safe; there is no global state besides the per-thread error string.
+ *  - return 0 on success, <0 on error (RS_E_*); rs_last_error() has the text.
+ *  - there is NO CPU fallback: rs_create fails if no CUDA device is usable.
+ *  - units on the wire follow the reference (Entities/Frame.py:8): m, m/s,
+ *    degrees, degrees/s; robot rows are blue ids first, then yellow
+ *    (rsim.py:96-99).
+ */
+#ifndef RSOCCER_B200_H
+#define RSOCCER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_OK 0
+#define RS_E_INVALID (-1)     /* bad argument */
+#define RS_E_CUDA (-2)        /* CUDA runtime error */
+#define RS_E_STATE (-3)       /* state buffer not bound */
+#define RS_E_UNSUPPORTED (-4) /* world/task combination not built */
+
+typedef struct rs_world rs_world;
+
+/* names of the SoA arrays inside the state buffer, for rs_layout */
+enum {
+    RS_ARR_BODY = 0,   /* float4 [R+1][Np]  (x, y, vx, vy); body 0 = ball, then robots */
+    RS_ARR_ANG = 1,    /* float2 [R][Np]    (theta [rad, (-pi, pi]], omega [rad/s]) */
+    RS_ARR_OU = 2,     /* float2 [R-1][Np]  OU process state of the non-agent robots (VSS-v0) */
+    RS_ARR_PREV = 3,   /* float  [Np]       previous ball potential (VSS-v0) */
+    RS_ARR_STEPS = 4,  /* int32  [Np]       episode step counter | has_prev << 24 */
+    RS_ARR_INFO = 5,   /* float  [9][Np]    reward_shaping_total accumulators */
+    RS_ARR_COUNT = 6
+};
+
+int rs_version(void);
+const char *rs_last_error(void);
+
+/* robosim.VSS / robosim.SSL constructor (rsim.py:116-124, 169-177).
+ * kind: 0 VSS, 1 SSL.  seed/env_offset key the on-device Philox streams by
+ * GLOBAL env id = env_offset + local index, so results do not depend on how
+ * envs are sharded over GPUs.  `device` < 0 keeps the current CUDA device. */
+int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_ms,
+              int n_envs, int device, uint64_t seed, int64_t env_offset, rs_world **out);
+/* RSim.stop (rsim.py:40-41) */
+int rs_destroy(rs_world *w);
+
+/* state memory is caller-owned: allocate rs_state_bytes() bytes of device memory
+ * (256-byte aligned), then bind it.  rs_bind_state zero-fills it and places the
+ * robots at the reference's dummy initial poses (rsim.py:19-24). */
+size_t rs_state_bytes(const rs_world *w);
+int rs_bind_state(rs_world *w, void *d_state, void *stream);
+/* byte offset of each RS_ARR_* array inside the state buffer and the padded env
+ * count Np (out_offsets[RS_ARR_COUNT], *out_np) so the caller can build views */
+int rs_layout(const rs_world *w, int64_t *out_offsets, int64_t *out_np);
+
+/* get_field_params (rsim.py:49-50): the 17 Field values in Entities/Field.py:5-21 order */
+int rs_field_params(const rs_world *w, double out[17]);
+
+/* simulator.reset (rsim.py:38): d_ball [N][4] = x y vx vy; d_blue [N][nb][3],
+ * d_yellow [N][ny][3] = x y theta_deg.  Robot velocities are zeroed, task state
+ * (OU, potential, step counter) cleared.  d_mask (nullable) [N] uint8: only
+ * envs with mask != 0 are touched. */
+int rs_reset(rs_world *w, const float *d_ball, const float *d_blue, const float *d_yellow,
+             const uint8_t *d_mask, void *stream);
+
+/* simulator.step (rsim.py:102 VSS: d_cmds [N][R][2] = wheel rad/s left,right;
+ * rsim.py:155 SSL: d_cmds [N][R][8] = flag, w0..w3 | vx vy vtheta 0, kick_x, kick_z, dribbler).
+ * Advances every env by one control step (5 sub-steps). */
+int rs_step(rs_world *w, const float *d_cmds, void *stream);
+
+/* simulator.get_state (rsim.py:105, 158): d_out [N][5 + K R] floats in the
+ * Entities/Frame.py layout (K = 6 VSS, 11 SSL) */
+int rs_get_state(const rs_world *w, float *d_out, void *stream);
+
+/* raw internal state in/out, [N][4 + 6 R] = ball x y vx vy, robot x y theta_rad
+ * vx vy omega (superset of reset: also sets robot velocities; checkpoint/restore
+ * and re-synced parity tests) */
+int rs_set_raw(rs_world *w, const float *d_in, void *stream);
+int rs_get_raw(const rs_world *w, float *d_out, void *stream);
+
+/* world step counter (Philox counter word 1); incremented by every step call */
+uint64_t rs_get_t(const rs_world *w);
+int rs_set_t(rs_world *w, uint64_t t);
+
+/* ---- task level: the env.step() of the benchmarked reference envs ---- */
+#define RS_TASK_VSS_V0 0
+#define RS_TASK_SSL_STATIC_DEFENDERS_V0 1
+#define RS_TASK_SSL_CONTESTED_POSSESSION_V0 2
+
+/* observation width of a task for this world (40 / 24 / 14 at the reference sizes) */
+int rs_task_obs_dim(const rs_world *w, int task);
+
+/* env.reset() for the envs selected by d_mask (nullable = all): random initial
+ * frame per the task's _get_initial_positions_frame, drawn on device; writes the
+ * first observation of the reset envs into d_obs (nullable) [N][obs_dim]. */
+int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, void *stream);
+
+/* VSSEnv.step for all N envs in one launch: OU commands for the 5 other robots,
+ * action -> wheel speeds, physics, observation, reward, done, TimeLimit
+ * truncation, reward_shaping_total, masked auto-reset.
+ *  d_actions [N][2] in [-1,1]; d_normals (nullable) [N][2(R-1)] standard normals
+ *  that replace the on-device Philox draw (parity harness); d_obs [N][40];
+ *  d_reward [N]; d_done [N]; d_trunc [N]; d_cmds_out (nullable) [N][R][2]. */
+int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals, int auto_reset,
+                    int max_steps, float *d_obs, float *d_reward, uint8_t *d_done,
+                    uint8_t *d_trunc, float *d_cmds_out, void *stream);
+
+/* SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step; d_actions [N][5] */
+int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_reset, int max_steps,
+                    float *d_obs, float *d_reward, uint8_t *d_done, uint8_t *d_trunc,
+                    float *d_cmds_out, void *stream);
+
+/* End-to-end variants with HOST buffers (what a binding holding numpy arrays
+ * calls): H2D copy of the actions, the fused step, D2H copy of obs / reward /
+ * done / trunc, then a stream synchronize.  Host buffers should be pinned. */
+int rs_vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset, int max_steps,
+                         float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc,
+                         void *stream);
+int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto_reset,
+                         int max_steps, float *h_obs, float *h_reward, uint8_t *h_done,
+                         uint8_t *h_trunc, void *stream);
+
+/* number of kernels this handle has launched so far (bench.py gpu_launches) */
+uint64_t rs_launch_count(const rs_world *w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSOCCER_B200_H */

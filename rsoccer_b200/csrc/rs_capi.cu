@@ -1,0 +1,794 @@
+// rs_capi.cu -- kernels + the C ABI declared in include/rsoccer_b200.h (sm_100a only).
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+//        -o rsoccer_b200/librsoccer_b200.so rsoccer_b200/csrc/rs_capi.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/rsoccer_b200.h"
+#include "rs_tasks.cuh"
+
+// ============================================================================ kernels
+
+struct VssStepArgs {
+    const float2 *actions;   // [N]
+    const float *normals;    // [N][2(R-1)] or null
+    float *obs;              // [N][NOBS]
+    float *reward;           // [N]
+    uint8_t *done, *trunc;   // [N]
+    float *cmds_out;         // [N][R][2] or null
+    int auto_reset, max_steps;
+    uint64_t seed;
+    uint32_t t, env_offset;
+};
+
+// VSSEnv.step for BS matches per CTA, one lane per match.  ONE launch = commands (agent +
+// OU noise), 5 physics sub-steps, reward/done/truncation, info accumulators, masked
+// auto-reset and the observation tile (leaves through a TMA bulk store).
+template <int NB, int NY, int BS>
+__global__ void __launch_bounds__(BS)
+k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
+    constexpr int R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
+    __shared__ __align__(128) float tile[BS * NOBS];
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * BS;
+    const int e = e0 + tid;
+    const int rows = min(BS, S.n - e0);
+    if (e < S.n) {
+        Scene<R> s;
+        load_scene<R>(P, S, e, s);
+        const int st = S.steps[e];
+        int steps = st & 0xFFFFFF;
+        bool has_prev = (st >> 24) & 1;
+        float prev = S.prev[e];
+        float info[RS_VSS_INFO];
+#pragma unroll
+        for (int i = 0; i < RS_VSS_INFO; ++i) info[i] = steps == 0 ? 0.0f : S.info[(size_t)i * S.np + e];
+        steps += 1;                                                 // vss_gym_base.py:73
+
+        // ---- _get_commands, vss_gym.py:119-142
+        Drive<R> d;
+        d.drib = 0;
+        const float2 act = A.actions[e];
+        float wl0, wr0;
+        vss_action_to_wheels(P, act.x, act.y, wl0, wr0);
+        vss_target(P, wl0, wr0, d.tf[0], d.tw[0]);
+        d.tl[0] = 0.0f; d.kick[0] = 0.0f;
+        if (A.cmds_out) { A.cmds_out[(size_t)e * R * 2] = wl0; A.cmds_out[(size_t)e * R * 2 + 1] = wr0; }
+        float z[NZ];
+        if (A.normals) {
+#pragma unroll
+            for (int k = 0; k < NZ; ++k) z[k] = A.normals[(size_t)e * NZ + k];
+        } else {
+            // Philox stream (global env id, t, OU): Box-Muller on consecutive u32 pairs
+            const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+#pragma unroll
+            for (int j = 0; j < (NZ + 3) / 4; ++j) {
+                const uint4 u = philox4x32_10(make_uint4(A.env_offset + (uint32_t)e, A.t, RS_STREAM_OU, j), key);
+                float sn, cs;
+                float rr = sqrtf(-2.0f * logf(u01(u.x)));
+                __sincosf(2.0f * RS_PI_F * (u01(u.y) - 0.5f), &sn, &cs);   // angle - pi: flip signs
+                if (4 * j < NZ) z[4 * j] = -rr * cs;
+                if (4 * j + 1 < NZ) z[4 * j + 1] = -rr * sn;
+                rr = sqrtf(-2.0f * logf(u01(u.z)));
+                __sincosf(2.0f * RS_PI_F * (u01(u.w) - 0.5f), &sn, &cs);
+                if (4 * j + 2 < NZ) z[4 * j + 2] = -rr * cs;
+                if (4 * j + 3 < NZ) z[4 * j + 3] = -rr * sn;
+            }
+        }
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            // Utils/Utils.py:14-21 OU sample (mu = 0, sigma = 0.5, theta = 0.17)
+            float2 ou = S.ou[(size_t)(r - 1) * S.np + e];
+            ou.x = ou.x + (float)RS_OU_THETA * (0.0f - ou.x) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z[2 * (r - 1)];
+            ou.y = ou.y + (float)RS_OU_THETA * (0.0f - ou.y) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z[2 * (r - 1) + 1];
+            S.ou[(size_t)(r - 1) * S.np + e] = ou;
+            float wl, wr;
+            vss_action_to_wheels(P, ou.x, ou.y, wl, wr);
+            vss_target(P, wl, wr, d.tf[r], d.tw[r]);
+            d.tl[r] = 0.0f; d.kick[r] = 0.0f;
+            if (A.cmds_out) { A.cmds_out[((size_t)e * R + r) * 2] = wl; A.cmds_out[((size_t)e * R + r) * 2 + 1] = wr; }
+        }
+
+        // ---- rsim.send_commands + get_frame, vss_gym_base.py:77-82
+        physics_step<RS_KIND_VSS, R>(P, s, d);
+
+        // ---- _calculate_reward_and_done, vss_gym.py:144-192
+        float rew; bool goal = false;
+        if (s.bx > P.half_len) { info[0] += 1.0f; info[4] += 1.0f; rew = 10.0f; goal = true; }
+        else if (s.bx < -P.half_len) { info[0] -= 1.0f; info[5] += 1.0f; rew = -10.0f; goal = true; }
+        else {
+            const float length_cm = 2.0f * P.half_len * 100.0f, hl = P.half_len + P.goal_depth;
+            const float dx_d = (hl + s.bx) * 100.0f, dx_a = (hl - s.bx) * 100.0f, dy = s.by * 100.0f;
+            const float pot = ((-sqrtf(dx_a * dx_a + 2.0f * dy * dy) + sqrtf(dx_d * dx_d + 2.0f * dy * dy)) / length_cm - 1.0f) * 0.5f;
+            float grad = 0.0f;
+            if (has_prev) grad = clampf((pot - prev) * 3.0f / P.dt, -5.0f, 5.0f);
+            prev = pot; has_prev = true;
+            const float rx = s.bx - s.x[0], ry = s.by - s.y[0];
+            const float rinv = rsqrtf(rx * rx + ry * ry);
+            const float move = clampf((rx * rinv * s.vx[0] + ry * rinv * s.vy[0]) * (1.0f / 0.4f), -5.0f, 5.0f);
+            const float energy = -(fabsf(wl0) + fabsf(wr0));
+            rew = 0.2f * move + 0.8f * grad + 2e-4f * energy;
+            info[1] += 0.2f * move; info[2] += 0.8f * grad; info[3] += 2e-4f * energy;
+        }
+        const bool tr = steps >= A.max_steps;                       // TimeLimit, __init__.py:4
+        A.reward[e] = rew; A.done[e] = goal ? 1 : 0; A.trunc[e] = tr ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < RS_VSS_INFO; ++i) S.info[(size_t)i * S.np + e] = info[i];
+
+        if (A.auto_reset && (goal || tr)) {                         // rare: stays out of the hot registers
+            Scene<0> tmp;
+            vss_place<0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, A.t, RS_STREAM_AUTORESET), tmp);
+            s.bx = tmp.bx; s.by = tmp.by; s.bvx = 0.0f; s.bvy = 0.0f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                s.x[r] = tmp.x[r]; s.y[r] = tmp.y[r]; s.th[r] = tmp.th[r];
+                s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+            }
+#pragma unroll
+            for (int r = 1; r < R; ++r) S.ou[(size_t)(r - 1) * S.np + e] = make_float2(0.0f, 0.0f);
+            steps = 0; has_prev = false; prev = 0.0f;
+        }
+        store_scene<R>(P, S, e, s);
+        S.steps[e] = steps | ((has_prev ? 1 : 0) << 24);
+        S.prev[e] = prev;
+        vss_obs<NB, NY>(P, s, tile + tid * NOBS);
+    }
+    tile_store(A.obs + (size_t)e0 * NOBS, tile, rows, NOBS);
+}
+
+struct SslStepArgs {
+    const float *actions;    // [N][5]
+    float *obs, *reward;
+    uint8_t *done, *trunc;
+    float *cmds_out;         // [N][R][8] or null
+    int auto_reset, max_steps;
+    uint64_t seed;
+    uint32_t t, env_offset;
+};
+
+// SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step
+template <int TASK, int NB, int NY, int BS>
+__global__ void __launch_bounds__(BS)
+k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
+    constexpr int R = NB + NY, NOBS = 4 + 8 * NB + 2 * NY;
+    __shared__ __align__(128) float tile[BS * NOBS];
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * BS;
+    const int e = e0 + tid;
+    const int rows = min(BS, S.n - e0);
+    if (e < S.n) {
+        Scene<R> s;
+        load_scene<R>(P, S, e, s);
+        int steps = S.steps[e] & 0xFFFFFF;
+        float info[RS_SSL_INFO];
+#pragma unroll
+        for (int i = 0; i < RS_SSL_INFO; ++i) info[i] = steps == 0 ? 0.0f : S.info[(size_t)i * S.np + e];
+        steps += 1;
+        // ---- _get_commands + convert_actions, static_defenders.py:114-148
+        float a[RS_SSL_ACT];
+#pragma unroll
+        for (int i = 0; i < RS_SSL_ACT; ++i) a[i] = A.actions[(size_t)e * RS_SSL_ACT + i];
+        const float max_v = 2.5f, max_w = 10.0f, kick_speed = 5.0f;
+        float cmd[8];
+        {
+            float sn, cs;
+            __sincosf(s.th[0], &sn, &cs);
+            const float vx = a[0] * max_v, vy = a[1] * max_v;
+            const float lx = vx * cs + vy * sn, ly = -vx * sn + vy * cs;
+            const float vn2 = lx * lx + ly * ly;
+            const float c = vn2 < max_v * max_v ? 1.0f : max_v * rsqrtf(vn2);
+            cmd[0] = 0.0f; cmd[1] = lx * c; cmd[2] = ly * c; cmd[3] = a[2] * max_w; cmd[4] = 0.0f;
+            cmd[5] = a[3] > 0.0f ? kick_speed : 0.0f; cmd[6] = 0.0f; cmd[7] = a[4] > 0.0f ? 1.0f : 0.0f;
+        }
+        Drive<R> d;
+        bool drib0;
+        ssl_target(P, cmd, d.tf[0], d.tl[0], d.tw[0], d.kick[0], drib0);
+        d.drib = drib0 ? 1u : 0u;
+#pragma unroll
+        for (int r = 1; r < R; ++r) { d.tf[r] = 0.0f; d.tl[r] = 0.0f; d.tw[r] = 0.0f; d.kick[r] = 0.0f; }
+        if (A.cmds_out) {
+            for (int i = 0; i < 8; ++i) A.cmds_out[(size_t)e * R * 8 + i] = cmd[i];
+            for (int i = 8; i < R * 8; ++i) A.cmds_out[(size_t)e * R * 8 + i] = 0.0f;
+        }
+        const float lbx = s.bx, lby = s.by, lrx = s.x[0], lry = s.y[0];   // last_frame
+
+        physics_step<RS_KIND_SSL, R>(P, s, d);
+
+        // ---- _calculate_reward_and_done, static_defenders.py:150-212 / contested_possession.py:136-208
+        float rew = 0.0f; bool dn = false;
+        if (TASK == RS_TASK_SSL_CONTESTED_POSSESSION) {
+#pragma unroll
+            for (int r = NB; r < R; ++r)
+                if (fabsf(s.vx[r]) > 0.1f || fabsf(s.vy[r]) > 0.1f) { info[8] += 1.0f; dn = true; }
+        }
+        const float hl = P.half_len, hw = P.half_wid;
+        if (s.x[0] < -0.2f || fabsf(s.y[0]) > hw) { dn = true; info[4] += 1.0f; }
+        else if (s.x[0] > hl - P.pen_len && fabsf(s.y[0]) < P.half_pen_wid) { dn = true; info[1] += 1.0f; }
+        else if (s.bx < 0.0f || fabsf(s.by) > hw) { dn = true; info[2] += 1.0f; }
+        else if (s.bx > hl) {
+            dn = true;
+            if (fabsf(s.by) < P.half_goal_wid) { rew = 5.0f; info[0] += 1.0f; } else { info[3] += 1.0f; }
+        } else {
+            const float ball_dist_scale = sqrtf(4.0f * hw * hw + hl * hl);
+            const float ball_grad_scale = sqrtf(hw * hw + hl * hl) * 0.25f;
+            const float energy_scale = 160.0f * 4.0f * (TASK == RS_TASK_SSL_STATIC_DEFENDERS ? 1000.0f : 1200.0f);
+            const float ld = sqrtf((lrx - lbx) * (lrx - lbx) + (lry - lby) * (lry - lby));
+            const float nd = sqrtf((s.x[0] - s.bx) * (s.x[0] - s.bx) + (s.y[0] - s.by) * (s.y[0] - s.by));
+            const float bd = clampf(ld - nd, -1.0f, 1.0f) / ball_dist_scale;
+            const float lg = sqrtf((hl - lbx) * (hl - lbx) + lby * lby);
+            const float ng = sqrtf((hl - s.bx) * (hl - s.bx) + s.by * s.by);
+            const float bg = clampf(lg - ng, -1.0f, 1.0f) / ball_grad_scale;
+            float sn, cs;
+            __sincosf(s.th[0], &sn, &cs);
+            const float vf = cs * s.vx[0] + sn * s.vy[0], vl = -sn * s.vx[0] + cs * s.vy[0];
+            float en = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) en += fabsf((P.J[i][0] * vf + P.J[i][1] * vl + P.J[i][2] * s.om[0]) * P.inv_rw);
+            const float er = -en / energy_scale;
+            info[5] += bd; info[6] += bg; info[7] += er;
+            rew = bd + bg + er;
+        }
+        const bool tr = steps >= A.max_steps;
+        A.reward[e] = rew; A.done[e] = dn ? 1 : 0; A.trunc[e] = tr ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < RS_SSL_INFO; ++i) S.info[(size_t)i * S.np + e] = info[i];
+        if (A.auto_reset && (dn || tr)) {
+            Scene<0> tmp;
+            task_place<TASK, 0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, A.t, RS_STREAM_AUTORESET), tmp);
+            s.bx = tmp.bx; s.by = tmp.by; s.bvx = 0.0f; s.bvy = 0.0f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                s.x[r] = tmp.x[r]; s.y[r] = tmp.y[r]; s.th[r] = tmp.th[r];
+                s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+            }
+            steps = 0;
+        }
+        store_scene<R>(P, S, e, s);
+        S.steps[e] = steps;
+        ssl_obs<NB, NY>(P, s, tile + tid * NOBS);
+    }
+    tile_store(A.obs + (size_t)e0 * NOBS, tile, rows, NOBS);
+}
+
+// simulator.step(cmds): physics only, any (kind, R).  RT > 0: register resident scene.
+template <int KIND, int RT, int BS>
+__global__ void __launch_bounds__(BS)
+k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__restrict__ cmds) {
+    const int e = blockIdx.x * BS + threadIdx.x;
+    if (e >= S.n) return;
+    const int R = RT > 0 ? RT : P.n_robots;
+    Scene<RT> s;
+    load_scene<RT>(P, S, e, s);
+    Drive<RT> d;
+    d.drib = 0;
+    if (KIND == RS_KIND_VSS) {
+        const float2 *c2 = reinterpret_cast<const float2 *>(cmds) + (size_t)e * R;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float2 c = c2[r];
+            vss_target(P, c.x, c.y, d.tf[r], d.tw[r]);
+            d.tl[r] = 0.0f; d.kick[r] = 0.0f;
+        }
+    } else {
+        const float4 *c4 = reinterpret_cast<const float4 *>(cmds) + (size_t)e * R * 2;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 lo = c4[2 * r], hi = c4[2 * r + 1];
+            const float cmd[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            bool drib;
+            ssl_target(P, cmd, d.tf[r], d.tl[r], d.tw[r], d.kick[r], drib);
+            if (drib) d.drib |= 1u << r;
+        }
+    }
+    physics_step<KIND, RT>(P, s, d);
+    store_scene<RT>(P, S, e, s);
+}
+
+// simulator.get_state(): Entities/Frame.py:20-47 / :55-93 rows, degrees on the wire
+__global__ void k_get_state(const DevParams P, const StatePtrs S, float *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n) return;
+    const int R = P.n_robots;
+    const int K = P.kind == RS_KIND_VSS ? RS_STATE_VSS_ROBOT : RS_STATE_SSL_ROBOT;
+    float *o = out + (size_t)e * (RS_STATE_BALL + K * R);
+    const float4 b = S.body[e];
+    o[0] = b.x; o[1] = b.y; o[2] = P.ball_r; o[3] = b.z; o[4] = b.w;
+    for (int r = 0; r < R; ++r) {
+        const float4 q = S.body[(size_t)(r + 1) * S.np + e];
+        const float2 a = S.ang[(size_t)r * S.np + e];
+        float *p = o + RS_STATE_BALL + K * r;
+        p[0] = q.x; p[1] = q.y; p[2] = a.x * RS_DEG_F; p[3] = q.z; p[4] = q.w; p[5] = a.y * RS_DEG_F;
+        if (P.kind == RS_KIND_SSL) {
+            float sn, cs;
+            __sincosf(a.x, &sn, &cs);
+            p[6] = touching(P, q.x, q.y, cs, sn, b.x, b.y) ? 1.0f : 0.0f;
+            const float vf = cs * q.z + sn * q.w, vl = -sn * q.z + cs * q.w;
+            for (int i = 0; i < 4; ++i) p[7 + i] = (P.J[i][0] * vf + P.J[i][1] * vl + P.J[i][2] * a.y) * P.inv_rw;
+        }
+    }
+}
+
+__device__ __forceinline__ void clear_task(const DevParams &P, const StatePtrs &S, int e) {
+    for (int r = 0; r + 1 < P.n_robots; ++r) S.ou[(size_t)r * S.np + e] = make_float2(0.0f, 0.0f);
+    S.prev[e] = 0.0f; S.steps[e] = 0;
+}
+
+// simulator.reset(ball, blue, yellow): rsim.py:36-38, 52-75
+__global__ void k_reset(const DevParams P, const StatePtrs S, const float *__restrict__ ball,
+                        const float *__restrict__ blue, const float *__restrict__ yellow,
+                        const uint8_t *__restrict__ mask) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n) return;
+    if (mask && !mask[e]) return;
+    const float4 b = reinterpret_cast<const float4 *>(ball)[e];
+    S.body[e] = b;
+    for (int r = 0; r < P.n_robots; ++r) {
+        const float *src = r < P.n_blue ? blue + ((size_t)e * P.n_blue + r) * 3
+                                        : yellow + ((size_t)e * P.n_yellow + (r - P.n_blue)) * 3;
+        float th = remainderf(src[2], 360.0f) * (1.0f / RS_DEG_F);
+        if (th <= -RS_PI_F) th += 2.0f * RS_PI_F;
+        S.body[(size_t)(r + 1) * S.np + e] = make_float4(src[0], src[1], 0.0f, 0.0f);
+        S.ang[(size_t)r * S.np + e] = make_float2(th, 0.0f);
+    }
+    clear_task(P, S, e);
+}
+
+// rsim.py:19-24 dummy initial poses after bind
+__global__ void k_init(const DevParams P, const StatePtrs S) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n) return;
+    S.body[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int r = 0; r < P.n_robots; ++r) {
+        const float x = r < P.n_blue ? -0.2f * (float)(r + 1) : 0.2f * (float)(r - P.n_blue + 1);
+        S.body[(size_t)(r + 1) * S.np + e] = make_float4(x, 0.0f, 0.0f, 0.0f);
+        S.ang[(size_t)r * S.np + e] = make_float2(0.0f, 0.0f);
+    }
+}
+
+__global__ void k_set_raw(const DevParams P, const StatePtrs S, const float *__restrict__ in) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n) return;
+    const float *r = in + (size_t)e * (4 + 6 * P.n_robots);
+    S.body[e] = make_float4(r[0], r[1], r[2], r[3]);
+    for (int k = 0; k < P.n_robots; ++k) {
+        const float *q = r + 4 + 6 * k;
+        S.body[(size_t)(k + 1) * S.np + e] = make_float4(q[0], q[1], q[3], q[4]);
+        S.ang[(size_t)k * S.np + e] = make_float2(q[2], q[5]);
+    }
+}
+__global__ void k_get_raw(const DevParams P, const StatePtrs S, float *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n) return;
+    float *r = out + (size_t)e * (4 + 6 * P.n_robots);
+    const float4 b = S.body[e];
+    r[0] = b.x; r[1] = b.y; r[2] = b.z; r[3] = b.w;
+    for (int k = 0; k < P.n_robots; ++k) {
+        const float4 q = S.body[(size_t)(k + 1) * S.np + e];
+        const float2 a = S.ang[(size_t)k * S.np + e];
+        float *o = r + 4 + 6 * k;
+        o[0] = q.x; o[1] = q.y; o[2] = a.x; o[3] = q.z; o[4] = q.w; o[5] = a.y;
+    }
+}
+
+// env.reset(): initial frame on device + first observation
+template <int TASK>
+__global__ void k_task_reset(const DevParams P, const StatePtrs S, const uint8_t *__restrict__ mask,
+                             float *__restrict__ obs, int obs_dim, uint64_t seed, uint32_t t,
+                             uint32_t env_offset) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n) return;
+    if (mask && !mask[e]) return;
+    Scene<0> s;
+    task_place<TASK, 0>(P, Rng(seed, env_offset + (uint32_t)e, t, RS_STREAM_RESET), s);
+    store_scene<0>(P, S, e, s);
+    clear_task(P, S, e);
+    if (!obs) return;
+    float *o = obs + (size_t)e * obs_dim;
+    int k = 0;
+    const int NB = P.n_blue, R = P.n_robots;
+    if (TASK == RS_TASK_VSS) {
+        o[k++] = nrm(s.bx, P.inv_max_pos); o[k++] = nrm(s.by, P.inv_max_pos);
+        o[k++] = nrm(s.bvx, P.inv_max_v); o[k++] = nrm(s.bvy, P.inv_max_v);
+        for (int r = 0; r < R; ++r) {
+            o[k++] = nrm(s.x[r], P.inv_max_pos); o[k++] = nrm(s.y[r], P.inv_max_pos);
+            if (r < NB) { float sn, cs; __sincosf(s.th[r], &sn, &cs); o[k++] = sn; o[k++] = cs; }
+            o[k++] = nrm(s.vx[r], P.inv_max_v); o[k++] = nrm(s.vy[r], P.inv_max_v);
+            o[k++] = nrm(s.om[r], P.inv_max_w_rad);
+        }
+    } else {
+        const float inv_v = 1.0f / 2.5f, inv_w = RS_DEG_F / 10.0f;
+        o[k++] = nrm(s.bx, P.inv_max_pos); o[k++] = nrm(s.by, P.inv_max_pos);
+        o[k++] = nrm(s.bvx, inv_v); o[k++] = nrm(s.bvy, inv_v);
+        for (int r = 0; r < NB; ++r) {
+            float sn, cs;
+            __sincosf(s.th[r], &sn, &cs);
+            o[k++] = nrm(s.x[r], P.inv_max_pos); o[k++] = nrm(s.y[r], P.inv_max_pos);
+            o[k++] = sn; o[k++] = cs;
+            o[k++] = nrm(s.vx[r], inv_v); o[k++] = nrm(s.vy[r], inv_v); o[k++] = nrm(s.om[r], inv_w);
+            o[k++] = touching(P, s.x[r], s.y[r], cs, sn, s.bx, s.by) ? 1.0f : 0.0f;
+        }
+        for (int r = NB; r < R; ++r) { o[k++] = nrm(s.x[r], P.inv_max_pos); o[k++] = nrm(s.y[r], P.inv_max_pos); }
+    }
+}
+
+// ============================================================================ host side
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                        \
+    do {                                                                                   \
+        cudaError_t _e = (x);                                                              \
+        if (_e != cudaSuccess)                                                             \
+            return fail(RS_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e));       \
+    } while (0)
+
+struct rs_world {
+    rs_params p;
+    DevParams dp;
+    int n, np, device;
+    uint64_t seed;
+    int64_t env_offset;
+    uint64_t t;
+    uint64_t launches;
+    void *state;
+    int64_t off[RS_ARR_COUNT];
+    size_t state_bytes;
+    int block;               // CTA size of the step kernels
+    // scratch for the *_host entry points (library owned)
+    float *s_actions, *s_obs, *s_reward;
+    uint8_t *s_done, *s_trunc;
+    int s_act_dim, s_obs_dim;
+};
+
+static void fill_dev_params(const rs_params &p, DevParams &d) {
+    memset(&d, 0, sizeof(d));
+    d.kind = p.kind; d.n_blue = p.n_blue; d.n_yellow = p.n_yellow; d.n_robots = p.n_robots;
+    d.dt = (float)p.dt; d.h = (float)p.h;
+    d.half_len = (float)(p.length / 2); d.half_wid = (float)(p.width / 2);
+    d.goal_depth = (float)p.goal_depth; d.pen_len = (float)p.penalty_length;
+    d.half_pen_wid = (float)(p.penalty_width / 2); d.half_goal_wid = (float)(p.goal_width / 2);
+    d.ball_r = (float)p.ball_radius; d.rbt_r = (float)p.rbt_radius;
+    d.rw = (float)p.rbt_wheel_radius; d.inv_rw = (float)(1.0 / p.rbt_wheel_radius);
+    d.wmax = (float)p.wheel_max_rad_s;
+    d.x_out = (float)p.x_out; d.y_out = (float)p.y_out; d.x_near = (float)p.x_near;
+    d.n_box = p.n_box;
+    for (int k = 0; k < RS_MAX_BOXES; ++k) for (int i = 0; i < 4; ++i) d.box[k][i] = (float)p.box[k][i];
+    const double wb = 1.0 / p.ball_mass, wr = 1.0 / p.rbt_mass;
+    d.wb = (float)wb; d.wr = (float)wr; d.inv_wsum = (float)(1.0 / (wb + wr));
+    d.fb = (float)(wb / (wb + wr)); d.fr = (float)(wr / (wb + wr));
+    d.e_ball_wall = (float)p.e_ball_wall; d.e_rbt_wall = (float)p.e_rbt_wall;
+    d.e_ball_rbt = (float)p.e_ball_rbt; d.e_rbt_rbt = (float)p.e_rbt_rbt;
+    d.mu_ball_rbt = (float)p.mu_ball_rbt;
+    d.ball_decel_h = (float)(p.ball_decel * p.h);
+    const double rs_br = p.rbt_radius + p.ball_radius, rs_rr = 2.0 * p.rbt_radius;
+    d.rs_br = (float)rs_br; d.rs_br2 = (float)(rs_br * rs_br);
+    d.rs_rr = (float)rs_rr; d.rs_rr2 = (float)(rs_rr * rs_rr);
+    d.inv_2b = p.half_track > 0 ? (float)(1.0 / (2.0 * p.half_track)) : 0.0f;
+    d.acc_fwd_h = (float)(p.acc_fwd * p.h); d.acc_lat_h = (float)(p.acc_lat * p.h);
+    d.acc_ang_h = (float)(p.acc_ang * p.h);
+    for (int i = 0; i < 4; ++i) for (int a = 0; a < 3; ++a) { d.J[i][a] = (float)p.omni_J[i][a]; d.Jp[a][i] = (float)p.omni_Jpinv[a][i]; }
+    d.dk = (float)p.rbt_distance_center_kicker; d.kick_centre = (float)p.kick_centre;
+    d.kick_reach = (float)p.kick_reach; d.kick_hw = (float)p.kick_half_width;
+    d.mouth_hc = (float)p.mouth_half_chord; d.kick_max = (float)p.kick_speed_max;
+    // vss_gym_base.py:52-58
+    const double PI = 3.14159265358979323846;
+    const double max_pos = p.width / 2 > p.length / 2 + p.penalty_length ? p.width / 2 : p.length / 2 + p.penalty_length;
+    const double max_v = (p.rbt_motor_max_rpm / 60.0) * 2.0 * PI * p.rbt_wheel_radius;
+    d.inv_max_pos = (float)(1.0 / max_pos); d.max_v = (float)max_v; d.inv_max_v = (float)(1.0 / max_v);
+    d.inv_max_w_rad = (float)(0.04 / max_v);       // omega[rad/s] * DEG / (rad2deg(max_v / 0.04))
+    d.sqrt_dt = (float)sqrt(p.dt);
+}
+
+static StatePtrs state_ptrs(const rs_world *w) {
+    StatePtrs S;
+    char *b = (char *)w->state;
+    S.body = (float4 *)(b + w->off[RS_ARR_BODY]);
+    S.ang = (float2 *)(b + w->off[RS_ARR_ANG]);
+    S.ou = (float2 *)(b + w->off[RS_ARR_OU]);
+    S.prev = (float *)(b + w->off[RS_ARR_PREV]);
+    S.steps = (int *)(b + w->off[RS_ARR_STEPS]);
+    S.info = (float *)(b + w->off[RS_ARR_INFO]);
+    S.n = w->n; S.np = w->np;
+    return S;
+}
+
+template <int KIND, int RT>
+static void launch_step(rs_world *w, const float *cmds, cudaStream_t st) {
+    const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
+    if (w->block == 128) k_step<KIND, RT, 128><<<g128, 128, 0, st>>>(w->dp, state_ptrs(w), cmds);
+    else k_step<KIND, RT, 64><<<g64, 64, 0, st>>>(w->dp, state_ptrs(w), cmds);
+}
+
+extern "C" {
+
+int rs_version(void) { return 100; }
+const char *rs_last_error(void) { return g_err.c_str(); }
+
+int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_ms, int n_envs,
+              int device, uint64_t seed, int64_t env_offset, rs_world **out) {
+    if (!out) return fail(RS_E_INVALID, "rs_create: out is null");
+    *out = nullptr;
+    if (n_envs < 1) return fail(RS_E_INVALID, "rs_create: n_envs must be >= 1");
+    if (env_offset < 0 || (uint64_t)env_offset + (uint64_t)n_envs > 0xFFFFFFFFull)
+        return fail(RS_E_INVALID, "rs_create: global env ids must fit 32 bits");
+    rs_params p;
+    if (rs_params_fill(&p, kind, field_type, n_blue, n_yellow, time_step_ms) != 0)
+        return fail(RS_E_INVALID, "rs_create: unknown world (kind/field_type) or bad robot counts");
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return fail(RS_E_CUDA, std::string("rs_create: no CUDA device (there is no CPU fallback): ") +
+                                   cudaGetErrorString(ce));
+    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+    else CUDA_TRY(cudaGetDevice(&device));
+    rs_world *w = new rs_world();
+    memset(w, 0, sizeof(*w));
+    w->p = p; fill_dev_params(p, w->dp);
+    w->n = n_envs; w->np = (n_envs + 127) / 128 * 128; w->device = device;
+    w->seed = seed; w->env_offset = env_offset; w->t = 0;
+    const int R = p.n_robots;
+    const size_t np = (size_t)w->np;
+    size_t o = 0;
+    w->off[RS_ARR_BODY] = (int64_t)o; o += 16 * (size_t)(R + 1) * np;
+    w->off[RS_ARR_ANG] = (int64_t)o; o += 8 * (size_t)R * np;
+    w->off[RS_ARR_OU] = (int64_t)o; o += 8 * (size_t)(R > 1 ? R - 1 : 1) * np;
+    w->off[RS_ARR_PREV] = (int64_t)o; o += 4 * np;
+    w->off[RS_ARR_STEPS] = (int64_t)o; o += 4 * np;
+    w->off[RS_ARR_INFO] = (int64_t)o; o += 4 * (size_t)RS_SSL_INFO * np;
+    w->state_bytes = o;
+    w->block = 64;
+    if (const char *bs = getenv("RS_BLOCK")) { const int b = atoi(bs); if (b == 32 || b == 64 || b == 128 || b == 256) w->block = b; }
+    *out = w;
+    return RS_OK;
+}
+
+int rs_destroy(rs_world *w) {
+    if (!w) return RS_OK;
+    cudaFree(w->s_actions); cudaFree(w->s_obs); cudaFree(w->s_reward); cudaFree(w->s_done); cudaFree(w->s_trunc);
+    delete w;
+    return RS_OK;
+}
+
+size_t rs_state_bytes(const rs_world *w) { return w ? w->state_bytes : 0; }
+
+int rs_layout(const rs_world *w, int64_t *out_offsets, int64_t *out_np) {
+    if (!w || !out_offsets || !out_np) return fail(RS_E_INVALID, "rs_layout: null argument");
+    for (int i = 0; i < RS_ARR_COUNT; ++i) out_offsets[i] = w->off[i];
+    *out_np = w->np;
+    return RS_OK;
+}
+
+int rs_bind_state(rs_world *w, void *d_state, void *stream) {
+    if (!w || !d_state) return fail(RS_E_INVALID, "rs_bind_state: null argument");
+    if ((uintptr_t)d_state & 255u) return fail(RS_E_INVALID, "rs_bind_state: buffer must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    w->state = d_state;
+    CUDA_TRY(cudaMemsetAsync(d_state, 0, w->state_bytes, st));
+    k_init<<<(w->n + 127) / 128, 128, 0, st>>>(w->dp, state_ptrs(w));
+    w->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_field_params(const rs_world *w, double out[17]) {
+    if (!w || !out) return fail(RS_E_INVALID, "rs_field_params: null argument");
+    rs_params_field(&w->p, out);
+    return RS_OK;
+}
+
+#define NEED_STATE(w, name)                                                                 \
+    if (!(w)) return fail(RS_E_INVALID, name ": null world");                               \
+    if (!(w)->state) return fail(RS_E_STATE, name ": no state buffer bound (rs_bind_state)")
+
+int rs_reset(rs_world *w, const float *d_ball, const float *d_blue, const float *d_yellow,
+             const uint8_t *d_mask, void *stream) {
+    NEED_STATE(w, "rs_reset");
+    if (!d_ball || (w->p.n_blue && !d_blue) || (w->p.n_yellow && !d_yellow))
+        return fail(RS_E_INVALID, "rs_reset: null placement array");
+    k_reset<<<(w->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dp, state_ptrs(w), d_ball, d_blue, d_yellow, d_mask);
+    w->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_step(rs_world *w, const float *d_cmds, void *stream) {
+    NEED_STATE(w, "rs_step");
+    if (!d_cmds) return fail(RS_E_INVALID, "rs_step: null commands");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = w->p.n_robots;
+    if (w->p.kind == RS_KIND_VSS) {
+        if (R == 6) launch_step<RS_KIND_VSS, 6>(w, d_cmds, st);
+        else if (R == 10) launch_step<RS_KIND_VSS, 10>(w, d_cmds, st);
+        else if (R == 2) launch_step<RS_KIND_VSS, 2>(w, d_cmds, st);
+        else launch_step<RS_KIND_VSS, 0>(w, d_cmds, st);
+    } else {
+        if (R == 7) launch_step<RS_KIND_SSL, 7>(w, d_cmds, st);
+        else if (R == 2) launch_step<RS_KIND_SSL, 2>(w, d_cmds, st);
+        else if (R == 1) launch_step<RS_KIND_SSL, 1>(w, d_cmds, st);
+        else launch_step<RS_KIND_SSL, 0>(w, d_cmds, st);
+    }
+    w->launches++; w->t++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_get_state(const rs_world *w, float *d_out, void *stream) {
+    NEED_STATE(w, "rs_get_state");
+    if (!d_out) return fail(RS_E_INVALID, "rs_get_state: null output");
+    k_get_state<<<(w->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dp, state_ptrs(w), d_out);
+    const_cast<rs_world *>(w)->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_set_raw(rs_world *w, const float *d_in, void *stream) {
+    NEED_STATE(w, "rs_set_raw");
+    if (!d_in) return fail(RS_E_INVALID, "rs_set_raw: null input");
+    k_set_raw<<<(w->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dp, state_ptrs(w), d_in);
+    w->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+int rs_get_raw(const rs_world *w, float *d_out, void *stream) {
+    NEED_STATE(w, "rs_get_raw");
+    if (!d_out) return fail(RS_E_INVALID, "rs_get_raw: null output");
+    k_get_raw<<<(w->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dp, state_ptrs(w), d_out);
+    const_cast<rs_world *>(w)->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+
+uint64_t rs_get_t(const rs_world *w) { return w ? w->t : 0; }
+int rs_set_t(rs_world *w, uint64_t t) {
+    if (!w) return fail(RS_E_INVALID, "rs_set_t: null world");
+    w->t = t;
+    return RS_OK;
+}
+uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches : 0; }
+
+static bool task_matches(const rs_world *w, int task) {
+    const rs_params &p = w->p;
+    if (task == RS_TASK_VSS_V0) return p.kind == RS_KIND_VSS && p.n_blue == 3 && p.n_yellow == 3;
+    if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) return p.kind == RS_KIND_SSL && p.n_blue == 1 && p.n_yellow == 6;
+    if (task == RS_TASK_SSL_CONTESTED_POSSESSION_V0) return p.kind == RS_KIND_SSL && p.n_blue == 1 && p.n_yellow == 1;
+    return false;
+}
+
+int rs_task_obs_dim(const rs_world *w, int task) {
+    if (!w) return fail(RS_E_INVALID, "rs_task_obs_dim: null world");
+    if (task == RS_TASK_VSS_V0) return 4 + 7 * w->p.n_blue + 5 * w->p.n_yellow;
+    if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0 || task == RS_TASK_SSL_CONTESTED_POSSESSION_V0)
+        return 4 + 8 * w->p.n_blue + 2 * w->p.n_yellow;
+    return fail(RS_E_INVALID, "rs_task_obs_dim: unknown task");
+}
+
+int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, void *stream) {
+    NEED_STATE(w, "rs_task_reset");
+    if (!task_matches(w, task)) return fail(RS_E_UNSUPPORTED, "rs_task_reset: task does not match this world");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = (w->n + 127) / 128, od = rs_task_obs_dim(w, task);
+    const uint32_t t = (uint32_t)w->t, off = (uint32_t)w->env_offset;
+    if (task == RS_TASK_VSS_V0) k_task_reset<RS_TASK_VSS><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
+    else if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) k_task_reset<RS_TASK_SSL_STATIC_DEFENDERS><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
+    else k_task_reset<RS_TASK_SSL_CONTESTED_POSSESSION><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
+    w->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals, int auto_reset,
+                    int max_steps, float *d_obs, float *d_reward, uint8_t *d_done,
+                    uint8_t *d_trunc, float *d_cmds_out, void *stream) {
+    NEED_STATE(w, "rs_vss_env_step");
+    if (!task_matches(w, RS_TASK_VSS_V0))
+        return fail(RS_E_UNSUPPORTED, "rs_vss_env_step: world is not VSS 3v3");
+    if (!d_actions || !d_obs || !d_reward || !d_done || !d_trunc)
+        return fail(RS_E_INVALID, "rs_vss_env_step: null argument");
+    if (max_steps < 1 || max_steps > 0xFFFFFF) return fail(RS_E_INVALID, "rs_vss_env_step: bad max_steps");
+    VssStepArgs A;
+    A.actions = reinterpret_cast<const float2 *>(d_actions); A.normals = d_normals;
+    A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.trunc = d_trunc; A.cmds_out = d_cmds_out;
+    A.auto_reset = auto_reset; A.max_steps = max_steps;
+    A.seed = w->seed; A.t = (uint32_t)w->t; A.env_offset = (uint32_t)w->env_offset;
+    cudaStream_t st = (cudaStream_t)stream;
+    const StatePtrs S = state_ptrs(w);
+    switch (w->block) {
+        case 32: k_vss_env_step<3, 3, 32><<<(w->n + 31) / 32, 32, 0, st>>>(w->dp, S, A); break;
+        case 128: k_vss_env_step<3, 3, 128><<<(w->n + 127) / 128, 128, 0, st>>>(w->dp, S, A); break;
+        case 256: k_vss_env_step<3, 3, 256><<<(w->n + 255) / 256, 256, 0, st>>>(w->dp, S, A); break;
+        default: k_vss_env_step<3, 3, 64><<<(w->n + 63) / 64, 64, 0, st>>>(w->dp, S, A); break;
+    }
+    w->launches++; w->t++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_reset, int max_steps,
+                    float *d_obs, float *d_reward, uint8_t *d_done, uint8_t *d_trunc,
+                    float *d_cmds_out, void *stream) {
+    NEED_STATE(w, "rs_ssl_env_step");
+    if ((task != RS_TASK_SSL_STATIC_DEFENDERS_V0 && task != RS_TASK_SSL_CONTESTED_POSSESSION_V0) || !task_matches(w, task))
+        return fail(RS_E_UNSUPPORTED, "rs_ssl_env_step: task does not match this world");
+    if (!d_actions || !d_obs || !d_reward || !d_done || !d_trunc)
+        return fail(RS_E_INVALID, "rs_ssl_env_step: null argument");
+    if (max_steps < 1 || max_steps > 0xFFFFFF) return fail(RS_E_INVALID, "rs_ssl_env_step: bad max_steps");
+    SslStepArgs A;
+    A.actions = d_actions; A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.trunc = d_trunc;
+    A.cmds_out = d_cmds_out; A.auto_reset = auto_reset; A.max_steps = max_steps;
+    A.seed = w->seed; A.t = (uint32_t)w->t; A.env_offset = (uint32_t)w->env_offset;
+    cudaStream_t st = (cudaStream_t)stream;
+    const StatePtrs S = state_ptrs(w);
+    const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
+    if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
+        if (w->block == 128) k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 128><<<g128, 128, 0, st>>>(w->dp, S, A);
+        else k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 64><<<g64, 64, 0, st>>>(w->dp, S, A);
+    } else {
+        if (w->block == 128) k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 128><<<g128, 128, 0, st>>>(w->dp, S, A);
+        else k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 64><<<g64, 64, 0, st>>>(w->dp, S, A);
+    }
+    w->launches++; w->t++;
+    CUDA_TRY(cudaGetLastError());
+    return RS_OK;
+}
+
+static int ensure_scratch(rs_world *w, int act_dim, int obs_dim) {
+    if (w->s_actions && w->s_act_dim == act_dim && w->s_obs_dim == obs_dim) return RS_OK;
+    cudaFree(w->s_actions); cudaFree(w->s_obs); cudaFree(w->s_reward); cudaFree(w->s_done); cudaFree(w->s_trunc);
+    w->s_actions = w->s_obs = w->s_reward = nullptr; w->s_done = w->s_trunc = nullptr;
+    CUDA_TRY(cudaMalloc(&w->s_actions, sizeof(float) * (size_t)w->n * act_dim));
+    CUDA_TRY(cudaMalloc(&w->s_obs, sizeof(float) * (size_t)w->n * obs_dim));
+    CUDA_TRY(cudaMalloc(&w->s_reward, sizeof(float) * (size_t)w->n));
+    CUDA_TRY(cudaMalloc(&w->s_done, (size_t)w->n));
+    CUDA_TRY(cudaMalloc(&w->s_trunc, (size_t)w->n));
+    w->s_act_dim = act_dim; w->s_obs_dim = obs_dim;
+    return RS_OK;
+}
+
+static int host_epilogue(rs_world *w, int obs_dim, float *h_obs, float *h_reward, uint8_t *h_done,
+                         uint8_t *h_trunc, cudaStream_t st) {
+    CUDA_TRY(cudaMemcpyAsync(h_obs, w->s_obs, sizeof(float) * (size_t)w->n * obs_dim, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_reward, w->s_reward, sizeof(float) * (size_t)w->n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_done, w->s_done, (size_t)w->n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_trunc, w->s_trunc, (size_t)w->n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return RS_OK;
+}
+
+int rs_vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset, int max_steps,
+                         float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc,
+                         void *stream) {
+    NEED_STATE(w, "rs_vss_env_step_host");
+    if (!h_actions || !h_obs || !h_reward || !h_done || !h_trunc)
+        return fail(RS_E_INVALID, "rs_vss_env_step_host: null argument");
+    const int od = rs_task_obs_dim(w, RS_TASK_VSS_V0);
+    int rc = ensure_scratch(w, RS_VSS_ACT, od);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(w->s_actions, h_actions, sizeof(float) * (size_t)w->n * RS_VSS_ACT, cudaMemcpyHostToDevice, st));
+    rc = rs_vss_env_step(w, w->s_actions, nullptr, auto_reset, max_steps, w->s_obs, w->s_reward, w->s_done, w->s_trunc, nullptr, stream);
+    if (rc) return rc;
+    return host_epilogue(w, od, h_obs, h_reward, h_done, h_trunc, st);
+}
+
+int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto_reset,
+                         int max_steps, float *h_obs, float *h_reward, uint8_t *h_done,
+                         uint8_t *h_trunc, void *stream) {
+    NEED_STATE(w, "rs_ssl_env_step_host");
+    if (!h_actions || !h_obs || !h_reward || !h_done || !h_trunc)
+        return fail(RS_E_INVALID, "rs_ssl_env_step_host: null argument");
+    const int od = rs_task_obs_dim(w, task);
+    if (od < 0) return od;
+    int rc = ensure_scratch(w, RS_SSL_ACT, od);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(w->s_actions, h_actions, sizeof(float) * (size_t)w->n * RS_SSL_ACT, cudaMemcpyHostToDevice, st));
+    rc = rs_ssl_env_step(w, task, w->s_actions, auto_reset, max_steps, w->s_obs, w->s_reward, w->s_done, w->s_trunc, nullptr, stream);
+    if (rc) return rc;
+    return host_epilogue(w, od, h_obs, h_reward, h_done, h_trunc, st);
+}
+
+}  // extern "C"

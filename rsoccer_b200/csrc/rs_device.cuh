@@ -1,0 +1,414 @@
+// rs_device.cuh -- device-side physics of the batched 2-D robot-soccer engine (sm_100a).
+//
+// One LANE per match ("env"): a warp advances 32 independent matches in lockstep,
+// the whole <= 23-body scene of a match lives in that lane's registers for all five
+// sub-steps, and HBM is touched once per control step (coalesced 128-bit loads /
+// stores of the SoA state).  DESIGN.md section 4 explains why this mapping beats a
+// warp-per-match mapping for the 7-body VSS scene (22 % lane use in the body phases).
+//
+// Replaces the arithmetic inside `robosim.VSS.step` / `robosim.SSL.step`
+// (reference call sites rsoccer_gym/Simulators/rsim.py:102, :155).  The model is
+// DESIGN.md section 3; oracle/rs_oracle.c restates it independently in fp64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rs_spec.h"
+
+#define RS_PI_F 3.14159265358979323846f
+#define RS_DEG_F 57.29577951308232f
+
+struct DevParams {
+    int kind, n_blue, n_yellow, n_robots;
+    float dt, h;
+    // field
+    float half_len, half_wid, goal_depth, pen_len, half_pen_wid, half_goal_wid;
+    float ball_r, rbt_r, rw, inv_rw, wmax;
+    // walls
+    float x_out, y_out, x_near;
+    int n_box;
+    float box[RS_MAX_BOXES][4];
+    // bodies
+    float wb, wr, inv_wsum, fb, fr;   // inverse masses, 1/(wb+wr), wb/(wb+wr), wr/(wb+wr)
+    float e_ball_wall, e_rbt_wall, e_ball_rbt, e_rbt_rbt, mu_ball_rbt;
+    float ball_decel_h;
+    float rs_br, rs_br2, rs_rr, rs_rr2;
+    // drive
+    float inv_2b, acc_fwd_h, acc_lat_h, acc_ang_h;
+    float J[4][3], Jp[3][4];
+    // kicker
+    float dk, kick_centre, kick_reach, kick_hw, mouth_hc, kick_max;
+    // task normalisers (vss_gym_base.py:52-58, 213-220)
+    float inv_max_pos, max_v, inv_max_v, inv_max_w_rad;  // obs w = clamp(omega[rad/s] * inv_max_w_rad)
+    float sqrt_dt;
+};
+
+template <int RT> struct Cap { static constexpr int v = RT > 0 ? RT : RS_MAX_ROBOTS; };
+
+// the scene of one match, register resident when RT > 0
+template <int RT>
+struct Scene {
+    float bx, by, bvx, bvy;
+    float x[Cap<RT>::v], y[Cap<RT>::v], vx[Cap<RT>::v], vy[Cap<RT>::v];
+    float th[Cap<RT>::v], om[Cap<RT>::v];
+};
+
+// per-robot drive targets in the robot frame + kicker / dribbler commands
+template <int RT>
+struct Drive {
+    float tf[Cap<RT>::v], tl[Cap<RT>::v], tw[Cap<RT>::v];
+    float kick[Cap<RT>::v];
+    uint32_t drib;   // bit r: dribbler on
+};
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float wrap_pi(float a) {
+    if (a > RS_PI_F) a -= 2.0f * RS_PI_F; else if (a <= -RS_PI_F) a += 2.0f * RS_PI_F;
+    return a;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+struct Rng {   // sequential u32 stream for (env, t, stream): counter (env, t, stream, j)
+    uint4 ctr; uint2 key; uint4 buf; int idx;
+    __device__ __forceinline__ Rng(uint64_t seed, uint32_t env, uint32_t t, uint32_t stream) {
+        key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        ctr = make_uint4(env, t, stream, 0u); idx = 4;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (idx == 4) { buf = philox4x32_10(ctr, key); ctr.w++; idx = 0; }
+        const uint32_t v = idx == 0 ? buf.x : idx == 1 ? buf.y : idx == 2 ? buf.z : buf.w;
+        ++idx; return v;
+    }
+    __device__ __forceinline__ float uniform(float a, float b) { return a + (b - a) * u01(next()); }
+};
+
+// ---------------------------------------------------------------- geometry
+// kicker "touching" box in the robot frame (lx, ly = ball centre, robot frame)
+__device__ __forceinline__ bool touching_local(const DevParams &P, float lx, float ly) {
+    return (fabsf(lx - P.kick_centre) < P.kick_reach) && (fabsf(ly) < P.kick_hw);
+}
+__device__ __forceinline__ bool touching(const DevParams &P, float rx, float ry, float c, float s,
+                                         float bx, float by) {
+    const float dx = bx - rx, dy = by - ry;
+    return touching_local(P, c * dx + s * dy, -s * dx + c * dy);
+}
+
+// walls for one body, mirrored quadrant
+__device__ __forceinline__ void walls(const DevParams &P, float r, float e, float &x, float &y,
+                                      float &vx, float &vy) {
+    float ax = fabsf(x), ay = fabsf(y);
+    if (ax + r <= P.x_near && ay <= P.y_out - r) return;   // interior: nothing to do
+    const float sx = x < 0.0f ? -1.0f : 1.0f, sy = y < 0.0f ? -1.0f : 1.0f;
+    float avx = sx * vx, avy = sy * vy;
+    if (ax + r > P.x_near) {
+#pragma unroll
+        for (int k = 0; k < RS_MAX_BOXES; ++k) {
+            if (k < P.n_box) {
+                const float lox = P.box[k][0], loy = P.box[k][1], hix = P.box[k][2], hiy = P.box[k][3];
+                const float qx = clampf(ax, lox, hix), qy = clampf(ay, loy, hiy);
+                const float dx = ax - qx, dy = ay - qy;
+                const float d2 = dx * dx + dy * dy;
+                if (d2 < r * r) {
+                    float nx, ny, pen;
+                    if (d2 > 1e-12f) {
+                        const float inv = rsqrtf(d2);
+                        nx = dx * inv; ny = dy * inv; pen = r - d2 * inv;
+                    } else {
+                        const float fxl = ax - lox, fxh = hix - ax, fyl = ay - loy, fyh = hiy - ay;
+                        float m = fxl; nx = -1.0f; ny = 0.0f;
+                        if (fxh < m) { m = fxh; nx = 1.0f; ny = 0.0f; }
+                        if (fyl < m) { m = fyl; nx = 0.0f; ny = -1.0f; }
+                        if (fyh < m) { m = fyh; nx = 0.0f; ny = 1.0f; }
+                        pen = r + m;
+                    }
+                    ax += pen * nx; ay += pen * ny;
+                    const float vn = avx * nx + avy * ny;
+                    if (vn < 0.0f) { avx -= (1.0f + e) * vn * nx; avy -= (1.0f + e) * vn * ny; }
+                }
+            }
+        }
+    }
+    if (ax > P.x_out - r) { ax = P.x_out - r; if (avx > 0.0f) avx = -e * avx; }
+    if (ay > P.y_out - r) { ay = P.y_out - r; if (avy > 0.0f) avy = -e * avy; }
+    x = sx * ax; y = sy * ay; vx = sx * avx; vy = sy * avy;
+}
+
+// robot <-> ball: detect on (rx, ry, rth) vs (bx, by); impulse on velocities, position
+// corrections accumulated into (cbx, cby) / (crx, cry)
+template <int KIND>
+__device__ __forceinline__ void ball_robot(const DevParams &P, float bx, float by, float &bvx,
+                                           float &bvy, float rx, float ry, float rth, float &rvx,
+                                           float &rvy, float rom, float &cbx, float &cby,
+                                           float &crx, float &cry, bool &any) {
+    const float dx = bx - rx, dy = by - ry;
+    const float d2 = dx * dx + dy * dy;
+    if (d2 >= P.rs_br2) return;
+    float nx, ny, pen, rcx, rcy;
+    if (KIND == RS_KIND_VSS) {
+        float d = 0.0f; nx = 1.0f; ny = 0.0f;
+        if (d2 > 1e-12f) { const float inv = rsqrtf(d2); nx = dx * inv; ny = dy * inv; d = d2 * inv; }
+        pen = P.rs_br - d;
+        rcx = nx * P.rbt_r; rcy = ny * P.rbt_r;
+    } else {
+        float s, c;
+        __sincosf(rth, &s, &c);
+        const float lx = c * dx + s * dy, ly = -s * dx + c * dy;
+        const float bn = sqrtf(d2);
+        float q1x = lx, q1y = ly;
+        if (bn > P.rbt_r) { const float k = P.rbt_r / bn; q1x = lx * k; q1y = ly * k; }
+        float qx, qy;
+        if (q1x <= P.dk) { qx = q1x; qy = q1y; }
+        else { qx = P.dk; qy = clampf(ly, -P.mouth_hc, P.mouth_hc); }
+        const float ex = lx - qx, ey = ly - qy;
+        const float e2 = ex * ex + ey * ey;
+        if (e2 >= P.ball_r * P.ball_r) return;
+        float lnx, lny;
+        if (e2 > 1e-12f) {
+            const float inv = rsqrtf(e2);
+            lnx = ex * inv; lny = ey * inv; pen = P.ball_r - e2 * inv;
+        } else {
+            const float pr = P.rbt_r - bn, pf = P.dk - lx;
+            if (pf < pr) { lnx = 1.0f; lny = 0.0f; pen = P.ball_r + pf; }
+            else {
+                if (bn > 1e-9f) { lnx = lx / bn; lny = ly / bn; } else { lnx = 1.0f; lny = 0.0f; }
+                pen = P.ball_r + pr;
+            }
+        }
+        nx = c * lnx - s * lny; ny = s * lnx + c * lny;
+        rcx = c * qx - s * qy; rcy = s * qx + c * qy;
+    }
+    const float sx = rvx - rom * rcy, sy = rvy + rom * rcx;   // robot surface velocity at contact
+    const float relx = bvx - sx, rely = bvy - sy;
+    const float vn = relx * nx + rely * ny;
+    if (vn < 0.0f) {
+        const float Jn = -(1.0f + P.e_ball_rbt) * vn * P.inv_wsum;
+        bvx += Jn * P.wb * nx; bvy += Jn * P.wb * ny;
+        rvx -= Jn * P.wr * nx; rvy -= Jn * P.wr * ny;
+        const float tx = -ny, ty = nx;
+        const float vt = relx * tx + rely * ty;
+        const float Jt = clampf(-vt * P.inv_wsum, -P.mu_ball_rbt * Jn, P.mu_ball_rbt * Jn);
+        bvx += Jt * P.wb * tx; bvy += Jt * P.wb * ty;
+        rvx -= Jt * P.wr * tx; rvy -= Jt * P.wr * ty;
+    }
+    cbx += pen * P.fb * nx; cby += pen * P.fb * ny;
+    crx -= pen * P.fr * nx; cry -= pen * P.fr * ny;
+    any = true;
+}
+
+__device__ __forceinline__ void robot_robot(const DevParams &P, float xi, float yi, float &vxi,
+                                            float &vyi, float xj, float yj, float &vxj, float &vyj,
+                                            float &cxi, float &cyi, float &cxj, float &cyj, bool &any) {
+    const float dx = xj - xi, dy = yj - yi;
+    const float d2 = dx * dx + dy * dy;
+    if (d2 >= P.rs_rr2) return;
+    float d = 0.0f, nx = 1.0f, ny = 0.0f;
+    if (d2 > 1e-12f) { const float inv = rsqrtf(d2); nx = dx * inv; ny = dy * inv; d = d2 * inv; }
+    const float pen = P.rs_rr - d;
+    const float vn = (vxj - vxi) * nx + (vyj - vyi) * ny;
+    if (vn < 0.0f) {
+        const float Jw = -(1.0f + P.e_rbt_rbt) * vn * 0.5f;   // J * wr with equal masses
+        vxi -= Jw * nx; vyi -= Jw * ny; vxj += Jw * nx; vyj += Jw * ny;
+    }
+    const float hp = 0.5f * pen;
+    cxi -= hp * nx; cyi -= hp * ny; cxj += hp * nx; cyj += hp * ny;
+    any = true;
+}
+
+// commands -> drive targets.  VSS: cmd = (wl, wr) rad/s (rsim.py:100-101)
+__device__ __forceinline__ void vss_target(const DevParams &P, float wl, float wr, float &tf, float &tw) {
+    wl = clampf(wl, -P.wmax, P.wmax); wr = clampf(wr, -P.wmax, P.wmax);
+    tf = P.rw * (wl + wr) * 0.5f;
+    tw = P.rw * (wr - wl) * P.inv_2b;
+}
+// SSL: cmd = 8 floats (rsim.py:137-153)
+__device__ __forceinline__ void ssl_target(const DevParams &P, const float (&cmd)[8], float &tf,
+                                           float &tl, float &tw, float &kick, bool &drib) {
+    float sp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float w;
+        if (cmd[0] != 0.0f) w = cmd[1 + i];
+        else w = (P.J[i][0] * cmd[1] + P.J[i][1] * cmd[2] + P.J[i][2] * cmd[3]) * P.inv_rw;
+        sp[i] = clampf(w, -P.wmax, P.wmax) * P.rw;
+    }
+    tf = P.Jp[0][0] * sp[0] + P.Jp[0][1] * sp[1] + P.Jp[0][2] * sp[2] + P.Jp[0][3] * sp[3];
+    tl = P.Jp[1][0] * sp[0] + P.Jp[1][1] * sp[1] + P.Jp[1][2] * sp[2] + P.Jp[1][3] * sp[3];
+    tw = P.Jp[2][0] * sp[0] + P.Jp[2][1] * sp[1] + P.Jp[2][2] * sp[2] + P.Jp[2][3] * sp[3];
+    kick = fminf(cmd[5], P.kick_max);
+    drib = cmd[7] != 0.0f;
+}
+
+// ---------------------------------------------------------------- one control step
+template <int KIND, int RT>
+__device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, const Drive<RT> &d) {
+    const int R = RT > 0 ? RT : P.n_robots;
+    const float h = P.h;
+    uint32_t kicked = 0;
+    if (KIND == RS_KIND_SSL) {
+        // kick: once per control step, robots in row order
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (d.kick[r] > 0.0f) {
+                float sn, cs;
+                __sincosf(s.th[r], &sn, &cs);
+                if (touching(P, s.x[r], s.y[r], cs, sn, s.bx, s.by)) {
+                    s.bvx = cs * d.kick[r]; s.bvy = sn * d.kick[r];
+                    kicked |= 1u << r;
+                }
+            }
+        }
+    }
+#pragma unroll 1
+    for (int k = 0; k < RS_SUBSTEPS; ++k) {
+        int holder = -1; float hx = 0.0f, hy = 0.0f;
+        // (a) drive, (b) dribbler latch
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float sn, cs;
+            __sincosf(s.th[r], &sn, &cs);
+            float vf = cs * s.vx[r] + sn * s.vy[r], vl = -sn * s.vx[r] + cs * s.vy[r];
+            if (KIND == RS_KIND_VSS) {
+                vf += clampf(d.tf[r] - vf, -P.acc_fwd_h, P.acc_fwd_h);
+                vl += clampf(d.tl[r] - vl, -P.acc_lat_h, P.acc_lat_h);
+            } else {
+                const float df = d.tf[r] - vf, dl = d.tl[r] - vl;
+                const float n2 = df * df + dl * dl;
+                float sc = 1.0f;
+                if (n2 > P.acc_fwd_h * P.acc_fwd_h) sc = P.acc_fwd_h * rsqrtf(n2);
+                vf += df * sc; vl += dl * sc;
+            }
+            s.om[r] += clampf(d.tw[r] - s.om[r], -P.acc_ang_h, P.acc_ang_h);
+            s.vx[r] = cs * vf - sn * vl; s.vy[r] = sn * vf + cs * vl;
+            if (KIND == RS_KIND_SSL) {
+                if (holder < 0 && ((d.drib >> r) & 1u) && !((kicked >> r) & 1u)) {
+                    const float dx = s.bx - s.x[r], dy = s.by - s.y[r];
+                    const float lx = cs * dx + sn * dy, ly = -sn * dx + cs * dy;
+                    if (touching_local(P, lx, ly)) { holder = r; hx = lx; hy = ly; }
+                }
+            }
+        }
+        // (c) ball rolling friction
+        if (holder < 0) {
+            const float sp2 = s.bvx * s.bvx + s.bvy * s.bvy;
+            const float sc = fmaxf(1.0f - P.ball_decel_h * rsqrtf(sp2 + 1e-12f), 0.0f);
+            s.bvx *= sc; s.bvy *= sc;
+        }
+        // (d) integrate
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            s.x[r] += s.vx[r] * h; s.y[r] += s.vy[r] * h;
+            s.th[r] = wrap_pi(s.th[r] + s.om[r] * h);
+        }
+        if (holder < 0) { s.bx += s.bvx * h; s.by += s.bvy * h; }
+        else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r == holder) {
+                    float sn, cs;
+                    __sincosf(s.th[r], &sn, &cs);
+                    const float ox = cs * hx - sn * hy, oy = sn * hx + cs * hy;
+                    s.bx = s.x[r] + ox; s.by = s.y[r] + oy;
+                    s.bvx = s.vx[r] - s.om[r] * oy; s.bvy = s.vy[r] + s.om[r] * ox;
+                }
+            }
+        }
+        // (e) pairs
+        {
+            float cbx = 0.0f, cby = 0.0f;
+            float cx[Cap<RT>::v], cy[Cap<RT>::v];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { cx[r] = 0.0f; cy[r] = 0.0f; }
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                ball_robot<KIND>(P, s.bx, s.by, s.bvx, s.bvy, s.x[r], s.y[r], s.th[r], s.vx[r],
+                                 s.vy[r], s.om[r], cbx, cby, cx[r], cy[r], any);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+#pragma unroll
+                for (int j = i + 1; j < R; ++j)
+                    robot_robot(P, s.x[i], s.y[i], s.vx[i], s.vy[i], s.x[j], s.y[j], s.vx[j],
+                                s.vy[j], cx[i], cy[i], cx[j], cy[j], any);
+            }
+            if (any) {
+                s.bx += cbx; s.by += cby;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { s.x[r] += cx[r]; s.y[r] += cy[r]; }
+            }
+        }
+        // (f) walls
+        walls(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
+#pragma unroll
+        for (int r = 0; r < R; ++r) walls(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
+    }
+}
+
+// ---------------------------------------------------------------- state I/O (SoA in HBM)
+struct StatePtrs {
+    float4 *body;     // [R+1][Np]
+    float2 *ang;      // [R][Np]
+    float2 *ou;       // [R-1][Np]
+    float *prev;      // [Np]
+    int *steps;       // [Np]
+    float *info;      // [RS_SSL_INFO][Np]
+    int n;            // envs
+    int np;           // padded env count (array pitch)
+};
+
+template <int RT>
+__device__ __forceinline__ void load_scene(const DevParams &P, const StatePtrs &S, int e, Scene<RT> &s) {
+    const int R = RT > 0 ? RT : P.n_robots;
+    const float4 b = S.body[e];
+    s.bx = b.x; s.by = b.y; s.bvx = b.z; s.bvy = b.w;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float4 q = S.body[(size_t)(r + 1) * S.np + e];
+        const float2 a = S.ang[(size_t)r * S.np + e];
+        s.x[r] = q.x; s.y[r] = q.y; s.vx[r] = q.z; s.vy[r] = q.w; s.th[r] = a.x; s.om[r] = a.y;
+    }
+}
+template <int RT>
+__device__ __forceinline__ void store_scene(const DevParams &P, const StatePtrs &S, int e, const Scene<RT> &s) {
+    const int R = RT > 0 ? RT : P.n_robots;
+    S.body[e] = make_float4(s.bx, s.by, s.bvx, s.bvy);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        S.body[(size_t)(r + 1) * S.np + e] = make_float4(s.x[r], s.y[r], s.vx[r], s.vy[r]);
+        S.ang[(size_t)r * S.np + e] = make_float2(s.th[r], s.om[r]);
+    }
+}
+
+// ---------------------------------------------------------------- smem tile -> global rows
+// Each thread has written its `row_floats` outputs to smem row `tid`; the tile of a CTA is
+// one contiguous span of global memory, so it leaves the SM as ONE TMA bulk copy
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP) when the span is 16-byte granular,
+// else as a coalesced cooperative copy.
+__device__ __forceinline__ void tile_store(float *gdst, const float *stile, int rows, int row_floats) {
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)row_floats * 4u;
+    if ((bytes & 15u) == 0u && ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0u)) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0 && bytes > 0) {
+            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stile);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else {
+        __syncthreads();
+        const int total = rows * row_floats;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) gdst[i] = stile[i];
+    }
+}

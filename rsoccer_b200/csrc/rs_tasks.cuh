@@ -1,0 +1,147 @@
+// rs_tasks.cuh -- device restatement of the task logic of the benchmarked reference envs
+// (commands, observation, reward, done, initial placement), fused into the step kernels.
+//   VSS-v0                      rsoccer_gym/vss/env_vss/vss_gym.py
+//   SSLStaticDefenders-v0       rsoccer_gym/ssl/ssl_hw_challenge/static_defenders.py
+//   SSLContestedPossession-v0   rsoccer_gym/ssl/ssl_hw_challenge/contested_possession.py
+#pragma once
+#include "rs_device.cuh"
+
+// vss_gym.py:235-254 _actions_to_v_wheels: action in [-1,1] -> wheel rad/s, clip, 0.05 m/s deadzone
+__device__ __forceinline__ void vss_action_to_wheels(const DevParams &P, float a0, float a1,
+                                                     float &wl, float &wr) {
+    float l = clampf(a0 * P.max_v, -P.max_v, P.max_v), r = clampf(a1 * P.max_v, -P.max_v, P.max_v);
+    if (-(float)RS_VSS_DEADZONE < l && l < (float)RS_VSS_DEADZONE) l = 0.0f;
+    if (-(float)RS_VSS_DEADZONE < r && r < (float)RS_VSS_DEADZONE) r = 0.0f;
+    wl = l * P.inv_rw; wr = r * P.inv_rw;
+}
+
+__device__ __forceinline__ float nrm(float v, float inv) {
+    return clampf(v * inv, -(float)RS_NORM_BOUNDS, (float)RS_NORM_BOUNDS);
+}
+
+// vss_gym.py:93-117 _frame_to_observations; o = row of 4 + 7 NB + 5 NY floats
+template <int NB, int NY>
+__device__ __forceinline__ void vss_obs(const DevParams &P, const Scene<NB + NY> &s, float *o) {
+    constexpr int NOBS = 4 + 7 * NB + 5 * NY;
+    float v[NOBS];
+    int k = 0;
+    v[k++] = nrm(s.bx, P.inv_max_pos); v[k++] = nrm(s.by, P.inv_max_pos);
+    v[k++] = nrm(s.bvx, P.inv_max_v); v[k++] = nrm(s.bvy, P.inv_max_v);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+        float sn, cs;
+        __sincosf(s.th[r], &sn, &cs);
+        v[k++] = nrm(s.x[r], P.inv_max_pos); v[k++] = nrm(s.y[r], P.inv_max_pos);
+        v[k++] = sn; v[k++] = cs;
+        v[k++] = nrm(s.vx[r], P.inv_max_v); v[k++] = nrm(s.vy[r], P.inv_max_v);
+        v[k++] = nrm(s.om[r], P.inv_max_w_rad);
+    }
+#pragma unroll
+    for (int r = NB; r < NB + NY; ++r) {
+        v[k++] = nrm(s.x[r], P.inv_max_pos); v[k++] = nrm(s.y[r], P.inv_max_pos);
+        v[k++] = nrm(s.vx[r], P.inv_max_v); v[k++] = nrm(s.vy[r], P.inv_max_v);
+        v[k++] = nrm(s.om[r], P.inv_max_w_rad);
+    }
+    if ((NOBS & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0u)) {
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+#pragma unroll
+        for (int i = 0; i < NOBS / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NOBS; ++i) o[i] = v[i];
+    }
+}
+
+// static_defenders.py:90-112 / contested_possession.py:78-105; row of 4 + 8 NB + 2 NY floats.
+// The reference divides v by the overridden max_v = 2.5 and v_theta [deg/s] by max_w = 10
+// (static_defenders.py:76-77) -- preserved.
+template <int NB, int NY>
+__device__ __forceinline__ void ssl_obs(const DevParams &P, const Scene<NB + NY> &s, float *o) {
+    int k = 0;
+    const float inv_v = 1.0f / 2.5f, inv_w = RS_DEG_F / 10.0f;
+    o[k++] = nrm(s.bx, P.inv_max_pos); o[k++] = nrm(s.by, P.inv_max_pos);
+    o[k++] = nrm(s.bvx, inv_v); o[k++] = nrm(s.bvy, inv_v);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+        float sn, cs;
+        __sincosf(s.th[r], &sn, &cs);
+        o[k++] = nrm(s.x[r], P.inv_max_pos); o[k++] = nrm(s.y[r], P.inv_max_pos);
+        o[k++] = sn; o[k++] = cs;
+        o[k++] = nrm(s.vx[r], inv_v); o[k++] = nrm(s.vy[r], inv_v);
+        o[k++] = nrm(s.om[r], inv_w);
+        o[k++] = touching(P, s.x[r], s.y[r], cs, sn, s.bx, s.by) ? 1.0f : 0.0f;
+    }
+#pragma unroll
+    for (int r = NB; r < NB + NY; ++r) { o[k++] = nrm(s.x[r], P.inv_max_pos); o[k++] = nrm(s.y[r], P.inv_max_pos); }
+}
+
+// ---- initial placement ----
+// vss_gym.py:194-233 (min_dist 0.1, exact all-pairs distance instead of the KD-tree)
+template <int RT>
+__device__ __noinline__ void vss_place(const DevParams &P, Rng g, Scene<RT> &s) {
+    const int R = RT > 0 ? RT : P.n_robots;
+    const float hl = P.half_len, hw = P.half_wid;
+    s.bx = g.uniform(-hl + 0.1f, hl - 0.1f); s.by = g.uniform(-hw + 0.1f, hw - 0.1f);
+    s.bvx = 0.0f; s.bvy = 0.0f;
+    for (int r = 0; r < R; ++r) {
+        float x = 0.0f, y = 0.0f;
+        for (int tries = 0; tries < 64; ++tries) {
+            x = g.uniform(-hl + 0.1f, hl - 0.1f); y = g.uniform(-hw + 0.1f, hw - 0.1f);
+            float dx = x - s.bx, dy = y - s.by;
+            bool ok = !(dx * dx + dy * dy < 0.01f);
+            for (int k = 0; k < r; ++k) {
+                dx = x - s.x[k]; dy = y - s.y[k];
+                if (dx * dx + dy * dy < 0.01f) ok = false;
+            }
+            if (ok) break;
+        }
+        s.x[r] = x; s.y[r] = y; s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+        s.th[r] = wrap_pi(g.uniform(0.0f, 360.0f) * (1.0f / RS_DEG_F));
+    }
+}
+// static_defenders.py:214-254
+template <int RT>
+__device__ __noinline__ void ssl_sd_place(const DevParams &P, Rng g, Scene<RT> &s) {
+    const int R = RT > 0 ? RT : P.n_robots;
+    const float hl = P.half_len, hw = P.half_wid;
+    s.x[0] = 0.0f; s.y[0] = 0.0f; s.th[0] = 0.0f; s.vx[0] = 0.0f; s.vy[0] = 0.0f; s.om[0] = 0.0f;
+    for (int tries = 0; tries < 64; ++tries) {
+        s.bx = g.uniform(0.2f, hl - 0.1f); s.by = g.uniform(-hw + 0.1f, hw - 0.1f);
+        if (!(s.bx > hl - P.pen_len && fabsf(s.by) < P.half_pen_wid)) break;
+    }
+    s.bvx = 0.0f; s.bvy = 0.0f;
+    for (int r = 1; r < R; ++r) {
+        float x = 0.0f, y = 0.0f;
+        for (int tries = 0; tries < 64; ++tries) {
+            x = g.uniform(0.2f, hl - 0.1f); y = g.uniform(-hw + 0.1f, hw - 0.1f);
+            float dx = x - s.bx, dy = y - s.by;
+            bool ok = !(dx * dx + dy * dy < 0.04f);
+            for (int k = 0; k < r; ++k) {
+                dx = x - s.x[k]; dy = y - s.y[k];
+                if (dx * dx + dy * dy < 0.04f) ok = false;
+            }
+            if (ok) break;
+        }
+        s.x[r] = x; s.y[r] = y; s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+        s.th[r] = wrap_pi(g.uniform(0.0f, 360.0f) * (1.0f / RS_DEG_F));
+    }
+}
+// contested_possession.py:210-227
+template <int RT>
+__device__ __noinline__ void ssl_cp_place(const DevParams &P, Rng g, Scene<RT> &s) {
+    const int R = RT > 0 ? RT : P.n_robots;
+    s.x[0] = 0.0f; s.y[0] = 0.0f; s.th[0] = 0.0f; s.vx[0] = 0.0f; s.vy[0] = 0.0f; s.om[0] = 0.0f;
+    const float ex = g.uniform(P.pen_len, P.half_len - P.pen_len);
+    const float ey = g.uniform(-P.half_pen_wid, P.half_pen_wid);
+    s.bx = ex - 0.1f; s.by = ey; s.bvx = 0.0f; s.bvy = 0.0f;
+    for (int r = 1; r < R; ++r) {
+        s.x[r] = ex; s.y[r] = ey + 0.5f * (float)(r - 1); s.th[r] = RS_PI_F;
+        s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+    }
+}
+template <int TASK, int RT>
+__device__ __forceinline__ void task_place(const DevParams &P, const Rng &g, Scene<RT> &s) {
+    if (TASK == RS_TASK_VSS) vss_place<RT>(P, g, s);
+    else if (TASK == RS_TASK_SSL_STATIC_DEFENDERS) ssl_sd_place<RT>(P, g, s);
+    else ssl_cp_place<RT>(P, g, s);
+}

@@ -1,0 +1,220 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle, same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from parity import TOL, check_close, random_raw, raw_diff
+
+pytestmark = pytest.mark.gpu
+
+
+def _worlds(E, O, kind, ft, nb, ny, n, seed=7, env_offset=0):
+    g = E.BatchedWorld(kind, ft, nb, ny, 25, n, seed=seed, env_offset=env_offset)
+    o = O.OracleWorld(kind, ft, nb, ny, 25, n, seed=seed, env_offset=env_offset, threads=8)
+    return g, o
+
+
+def _random_cmds(rng, kind, n, R):
+    if kind == 0:
+        c = rng.uniform(-60, 60, (n, R, 2))
+        c[rng.random((n, R)) < 0.2] = 0.0
+        return c.astype(np.float32)
+    c = np.zeros((n, R, 8), dtype=np.float32)
+    c[:, :, 1:3] = rng.uniform(-2.5, 2.5, (n, R, 2))
+    c[:, :, 3] = rng.uniform(-10, 10, (n, R))
+    ws = rng.random((n, R)) < 0.2
+    c[ws, 0] = 1.0
+    c[ws, 1:5] = rng.uniform(-150, 150, (int(ws.sum()), 4))
+    c[:, :, 5] = np.where(rng.random((n, R)) < 0.3, 5.0, 0.0)
+    c[:, :, 7] = (rng.random((n, R)) < 0.4).astype(np.float32)
+    c[rng.random((n, R)) < 0.2] = 0.0
+    return c
+
+
+@pytest.mark.parametrize("kind,ft,nb,ny", [(0, 0, 3, 3), (0, 1, 5, 5), (0, 0, 1, 1), (0, 0, 2, 3),
+                                           (1, 2, 1, 6), (1, 2, 1, 1), (1, 0, 3, 3), (1, 2, 1, 0)])
+def test_step_parity_resynced(engine, oracle, kind, ft, nb, ny):
+    """rs_step vs oracle, one control step from identical random (contact-rich) states."""
+    E, O = engine, oracle
+    n, R = 4096, nb + ny
+    g, o = _worlds(E, O, kind, ft, nb, ny, n)
+    fp = o.field_params()
+    rng = np.random.default_rng(1234 + 10 * kind + R)
+    worst = 0.0
+    for it in range(6):
+        raw = random_raw(rng, n, R, fp["length"] / 2 + 0.05, fp["width"] / 2,
+                         v_ball=2.0 if kind else 1.0, v_rbt=1.0, w_rbt=6.0)
+        if kind == 1 and it % 2 == 1:   # put the ball in front of robot 0's mouth in half the envs
+            k = rng.random(n) < 0.5
+            th = raw[:, 4 + 2]
+            d = rng.uniform(0.085, 0.115, n)
+            lat = rng.uniform(-0.05, 0.05, n)
+            raw[k, 0] = (raw[:, 4] + np.cos(th) * d - np.sin(th) * lat)[k]
+            raw[k, 1] = (raw[:, 5] + np.sin(th) * d + np.cos(th) * lat)[k]
+            raw = raw.astype(np.float32).astype(np.float64)
+        cmds = _random_cmds(rng, kind, n, R)
+        g.set_raw(raw); o.set_raw(raw)
+        g.step(cmds); o.step(cmds.astype(np.float64))
+        err = raw_diff(g.get_raw().cpu().numpy(), o.get_raw(), R)
+        w, fl = check_close(err, o.margin(), "step kind=%d R=%d it=%d" % (kind, R, it))
+        worst = max(worst, w)
+        # the wire format agrees too (degrees, infrared, wheel speeds)
+        sg, so = g.get_state().cpu().numpy().astype(np.float64), o.get_state()
+        K = 6 if kind == 0 else 11
+        ok = o.margin() >= 2e-5
+        ds = np.abs(sg - so)
+        for r in range(R):
+            c = 5 + K * r + 2
+            ds[:, c] = np.abs((sg[:, c] - so[:, c] + 180.0) % 360.0 - 180.0)
+        tol = np.full(sg.shape[1], TOL)
+        for r in range(R):
+            tol[5 + K * r + 2] = 1e-2          # degrees
+            tol[5 + K * r + 5] = 2e-2          # degrees / s
+            if kind == 1:
+                tol[5 + K * r + 7:5 + K * r + 11] = 5e-3   # wheel rad/s = v / 0.02475
+        assert (ds[ok] <= tol).all(), "get_state mismatch %s" % np.argwhere(ds[ok] > tol)[:5]
+    print("worst abs err", worst)
+
+
+def test_step_parity_free_running(engine, oracle):
+    """40 control steps without re-sync, contact-free envs stay within 1e-3."""
+    E, O = engine, oracle
+    n, R = 2048, 6
+    g, o = _worlds(E, O, 0, 0, 3, 3, n)
+    rng = np.random.default_rng(5)
+    ball = np.zeros((n, 4)); ball[:, 0] = rng.uniform(-0.1, 0.1, n); ball[:, 1] = 0.55
+    ball[:, 2] = rng.uniform(-0.3, 0.3, n)
+    xs = np.array([-0.5, -0.3, -0.1, 0.1, 0.3, 0.5])
+    rob = np.zeros((n, 6, 3)); rob[:, :, 0] = xs; rob[:, :, 1] = rng.uniform(-0.3, 0.2, (n, 6))
+    rob[:, :, 2] = rng.uniform(60, 120, (n, 6))
+    ball = ball.astype(np.float32); rob = rob.astype(np.float32)
+    g.reset(ball, rob[:, :3], rob[:, 3:]); o.reset(ball, rob[:, :3], rob[:, 3:])
+    cmds = rng.uniform(5, 25, (n, 6, 2)).astype(np.float32)
+    cmds[:, :, 1] = cmds[:, :, 0] + rng.uniform(-1, 1, (n, 6))
+    mmin = np.full(n, 1e9)
+    for _ in range(10):
+        g.step(cmds); o.step(cmds.astype(np.float64))
+        mmin = np.minimum(mmin, o.margin())
+    err = raw_diff(g.get_raw().cpu().numpy(), o.get_raw(), R)
+    ok = mmin > 1e-3
+    assert ok.mean() > 0.5
+    assert err[ok].max() < 1e-3, err[ok].max()
+
+
+def _sync_task(g, o, R):
+    raw = g.get_raw().cpu().numpy().astype(np.float64)
+    o.set_raw(raw)
+    st = g.steps[:g.n].cpu().numpy()
+    ou = g.ou[:, :g.n, :].permute(1, 0, 2).reshape(g.n, -1).cpu().numpy().astype(np.float64)
+    o.set_task_state(ou=ou[:, :2 * (R - 1)], prev_pot=g.prev_pot[:g.n].cpu().numpy().astype(np.float64),
+                     has_prev=((st >> 24) & 1).astype(np.int32), steps=(st & 0xFFFFFF).astype(np.int32),
+                     info=g.info[:, :g.n].t().cpu().numpy().astype(np.float64))
+    o.t = g.t
+
+
+def test_vss_env_step_parity(engine, oracle):
+    """Fused VSSEnv.step (Philox OU noise, reward, done, auto-reset, obs) vs the oracle,
+    re-synced each step, 60 steps, with short episodes so auto-reset is exercised."""
+    E, O = engine, oracle
+    n, R = 4096, 6
+    g, o = _worlds(E, O, 0, 0, 3, 3, n, seed=99, env_offset=1000)
+    g.task_reset(E.TASK_VSS_V0)
+    _sync_task(g, o, R)
+    # device placement == oracle placement on the same stream
+    o2 = O.OracleWorld(0, 0, 3, 3, 25, n, seed=99, env_offset=1000)
+    o2.task_reset(O.TASK_VSS)
+    assert raw_diff(g.get_raw().cpu().numpy(), o2.get_raw(), R).max() < 1e-5
+    rng = np.random.default_rng(3)
+    worst = {"obs": 0.0, "rew": 0.0, "raw": 0.0}
+    n_done = 0
+    for it in range(60):
+        if it == 20:   # speed things up: balls heading for the goals
+            raw = g.get_raw().cpu().numpy()
+            raw[:, 0] = rng.uniform(0.55, 0.7, n) * rng.choice([-1, 1], n)
+            raw[:, 1] = rng.uniform(-0.15, 0.15, n)
+            raw[:, 2] = np.sign(raw[:, 0]) * rng.uniform(0.5, 2.0, n)
+            g.set_raw(raw)
+        _sync_task(g, o, R)
+        act = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        cg = torch.zeros(n, R, 2, device="cuda")
+        obs, rew, done, trunc = g.vss_env_step(act, max_steps=25, cmds_out=cg)
+        oobs, orew, odone, otrunc, ocmd = o.vss_env_step(act, max_steps=25, want_cmds=True)
+        m = o.margin()
+        ok = m >= 2e-5
+        assert (np.abs(cg.cpu().numpy() - ocmd)[ok].max()) < 2e-3       # rad/s
+        assert (done.cpu().numpy()[ok] == odone[ok]).all()
+        assert (trunc.cpu().numpy() == otrunc).all()
+        n_done += int(odone.sum() + otrunc.sum())
+        e_obs = np.abs(obs.cpu().numpy() - oobs).max(axis=1)
+        e_rew = np.abs(rew.cpu().numpy() - orew)
+        e_raw = raw_diff(g.get_raw().cpu().numpy(), o.get_raw(), R)
+        worst["obs"] = max(worst["obs"], check_close(e_obs, m, "obs it=%d" % it)[0])
+        worst["rew"] = max(worst["rew"], check_close(e_rew, m, "reward it=%d" % it, tol=2e-4)[0])
+        worst["raw"] = max(worst["raw"], check_close(e_raw, m, "state it=%d" % it)[0])
+        ts = o.get_task_state()
+        st = g.steps[:n].cpu().numpy()
+        assert ((st & 0xFFFFFF)[ok] == ts["steps"][ok]).all()
+        gi = g.info[:, :n].t().cpu().numpy()
+        assert np.abs(gi - ts["info"])[ok].max() < 2e-3
+    assert n_done > n          # every env was reset at least once on average
+    print("worst", worst, "resets", n_done)
+
+
+@pytest.mark.parametrize("task,nb,ny,max_steps", [(1, 1, 6, 30), (2, 1, 1, 30)])
+def test_ssl_env_step_parity(engine, oracle, task, nb, ny, max_steps):
+    E, O = engine, oracle
+    n, R = 4096, nb + ny
+    g, o = _worlds(E, O, 1, 2, nb, ny, n, seed=5, env_offset=77)
+    g.task_reset(task)
+    o2 = O.OracleWorld(1, 2, nb, ny, 25, n, seed=5, env_offset=77)
+    o2.task_reset(task)
+    assert raw_diff(g.get_raw().cpu().numpy(), o2.get_raw(), R).max() < 1e-5
+    rng = np.random.default_rng(11)
+    worst = {"obs": 0.0, "rew": 0.0, "raw": 0.0}
+    n_done = 0
+    for it in range(50):
+        _sync_task(g, o, R)
+        act = rng.uniform(-1, 1, (n, 5)).astype(np.float32)
+        if it % 3 == 0:       # chase the ball with dribbler on to exercise hold + kick
+            raw = g.get_raw().cpu().numpy()
+            d = raw[:, 0:2] - raw[:, 4:6]
+            act[:, 0:2] = d / (np.linalg.norm(d, axis=1, keepdims=True) + 1e-6)
+            act[:, 4] = 1.0
+        cg = torch.zeros(n, R, 8, device="cuda")
+        obs, rew, done, trunc = g.ssl_env_step(task, act, max_steps=max_steps, cmds_out=cg)
+        oobs, orew, odone, otrunc, ocmd = o.ssl_env_step(task, act, max_steps=max_steps, want_cmds=True)
+        m = o.margin()
+        ok = m >= 2e-5
+        assert np.abs(cg.cpu().numpy() - ocmd)[ok].max() < 1e-4
+        assert (done.cpu().numpy()[ok] == odone[ok]).all()
+        assert (trunc.cpu().numpy() == otrunc).all()
+        n_done += int(odone.sum() + otrunc.sum())
+        e_obs = np.abs(obs.cpu().numpy() - oobs).max(axis=1)
+        e_rew = np.abs(rew.cpu().numpy() - orew)
+        e_raw = raw_diff(g.get_raw().cpu().numpy(), o.get_raw(), R)
+        worst["obs"] = max(worst["obs"], check_close(e_obs, m, "obs it=%d" % it, max_flagged=0.05)[0])
+        worst["rew"] = max(worst["rew"], check_close(e_rew, m, "reward it=%d" % it, max_flagged=0.05)[0])
+        worst["raw"] = max(worst["raw"], check_close(e_raw, m, "state it=%d" % it, max_flagged=0.05)[0])
+    assert n_done > n
+    print("worst", worst, "resets", n_done)
+
+
+def test_batch_vs_single_and_shard_invariance(engine):
+    """env i of a batch == the same env alone; results do not depend on the sharding."""
+    E = engine
+    n = 512
+    big = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=3, env_offset=0)
+    lo = E.BatchedWorld(0, 0, 3, 3, 25, n // 2, seed=3, env_offset=0)
+    hi = E.BatchedWorld(0, 0, 3, 3, 25, n // 2, seed=3, env_offset=n // 2)
+    for w in (big, lo, hi):
+        w.task_reset(E.TASK_VSS_V0)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for _ in range(30):
+        a = (torch.rand(n, 2, generator=g) * 2 - 1).cuda()
+        ob, rb, db, tb = big.vss_env_step(a, max_steps=10)
+        ol, rl, dl, tl = lo.vss_env_step(a[:n // 2], max_steps=10)
+        oh, rh, dh, th = hi.vss_env_step(a[n // 2:], max_steps=10)
+        assert torch.equal(ob, torch.cat([ol, oh]))
+        assert torch.equal(rb, torch.cat([rl, rh]))
+        assert torch.equal(db, torch.cat([dl, dh]))
+    assert torch.equal(big.get_raw(), torch.cat([lo.get_raw(), hi.get_raw()]))
