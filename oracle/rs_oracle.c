@@ -108,6 +108,10 @@ static double wrap_pi(double a) {
     return a;
 }
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+/* a contact normal n = delta/|delta| amplifies an input perturbation eps to eps/|delta|;
+ * scaled so that |delta| < 5 mm (only reachable by injecting overlapping bodies, the
+ * dynamics keep centres >= one radius apart) counts as ill conditioned at margin 2e-5 */
+#define NORMAL_COND 4e-3
 static void note(double *margin, double m) { m = fabs(m); if (m < *margin) *margin = m; }
 
 /* kicker "touching" box, in the robot frame (grSim isTouchingBall analogue).
@@ -143,6 +147,7 @@ static int ball_robot_contact(const rs_params *p, const o_robot *r, const o_ball
         note(margin, sqrt(d2) - rs);
         if (d2 >= rs * rs) return 0;
         double d = sqrt(d2);
+        note(margin, d * NORMAL_COND);
         if (d2 > 1e-12) { *nx = dx / d; *ny = dy / d; } else { *nx = 1.0; *ny = 0.0; d = 0.0; }
         *pen = rs - d;
         *rcx = *nx * R; *rcy = *ny * R;
@@ -165,9 +170,11 @@ static int ball_robot_contact(const rs_params *p, const o_robot *r, const o_ball
     double lnx, lny;
     if (e2 > 1e-12) {
         double e = sqrt(e2);
+        note(margin, e * NORMAL_COND);
         lnx = ex / e; lny = ey / e; *pen = rb - e;
     } else {                     /* ball centre inside the robot shape: least-penetration exit */
         double pr = R - bn, pf = dk - lx;
+        note(margin, 0.0);       /* unreachable by the dynamics; never well conditioned */
         if (pf < pr) { lnx = 1.0; lny = 0.0; *pen = rb + pf; }
         else {
             if (bn > 1e-9) { lnx = lx / bn; lny = ly / bn; } else { lnx = 1.0; lny = 0.0; }
@@ -196,8 +203,10 @@ static void walls(const rs_params *p, double r, double e, double *x, double *y,
             double nx, ny, pen;
             if (d2 > 1e-12) {
                 double d = sqrt(d2);
+                note(margin, d * NORMAL_COND);
                 nx = dx / d; ny = dy / d; pen = r - d;
             } else {
+                note(margin, 0.0);
                 double fxl = ax - bx[0], fxh = bx[2] - ax, fyl = ay - bx[1], fyh = bx[3] - ay;
                 double m = fxl; nx = -1.0; ny = 0.0;
                 if (fxh < m) { m = fxh; nx = 1.0; ny = 0.0; }
@@ -351,6 +360,7 @@ static void step_env(const rs_params *p, o_ball *b, o_robot *rb, const double *c
             note(margin, sqrt(d2) - rs);
             if (d2 >= rs * rs) continue;
             double d = sqrt(d2), nx, ny;
+            note(margin, d * NORMAL_COND);
             if (d2 > 1e-12) { nx = dx / d; ny = dy / d; } else { nx = 1.0; ny = 0.0; d = 0.0; }
             double pen = rs - d;
             double vn = (rb[j].vx - rb[i].vx) * nx + (rb[j].vy - rb[i].vy) * ny;
