@@ -117,6 +117,10 @@ int rs_get_raw(const rs_world *w, float *d_out, void *stream);
 /* world step counter (Philox counter word 1); incremented by every step call */
 uint64_t rs_get_t(const rs_world *w);
 int rs_set_t(rs_world *w, uint64_t t);
+/* The counter the kernels read lives in device memory (so a captured CUDA graph replays
+ * with fresh Philox counters); rs_get_t returns the host mirror, which is exact unless
+ * launches were replayed from a graph -- rs_sync_t reads the device value back (blocking). */
+int rs_sync_t(rs_world *w, void *stream);
 
 /* ---- task level: the env.step() of the benchmarked reference envs ---- */
 #define RS_TASK_VSS_V0 0

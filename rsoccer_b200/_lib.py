@@ -27,7 +27,7 @@ TASK_VSS_V0, TASK_SSL_STATIC_DEFENDERS_V0, TASK_SSL_CONTESTED_POSSESSION_V0 = 0,
 SYMBOLS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_state_bytes", "rs_bind_state",
     "rs_layout", "rs_field_params", "rs_reset", "rs_step", "rs_get_state", "rs_set_raw",
-    "rs_get_raw", "rs_get_t", "rs_set_t", "rs_task_obs_dim", "rs_task_reset", "rs_vss_env_step",
+    "rs_get_raw", "rs_get_t", "rs_set_t", "rs_sync_t", "rs_task_obs_dim", "rs_task_reset", "rs_vss_env_step",
     "rs_ssl_env_step", "rs_vss_env_step_host", "rs_ssl_env_step_host", "rs_launch_count",
 )
 
@@ -88,6 +88,7 @@ def lib():
     L.rs_get_t.restype = u64
     L.rs_get_t.argtypes = [vp]
     L.rs_set_t.argtypes = [vp, u64]
+    L.rs_sync_t.argtypes = [vp, vp]
     L.rs_task_obs_dim.argtypes = [vp, i32]
     L.rs_task_reset.argtypes = [vp, i32, vp, vp, vp]
     L.rs_vss_env_step.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]

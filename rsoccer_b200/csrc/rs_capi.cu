@@ -13,6 +13,17 @@
 
 // ============================================================================ kernels
 
+// The world step counter lives in device memory so that a captured CUDA graph replays
+// with fresh Philox counters: every CTA reads ctr[0] on entry, the last CTA to finish
+// bumps it (all CTAs have read it by then; the next launch is stream ordered).
+__device__ __forceinline__ void bump_step_counter(uint32_t *ctr, uint32_t t) {
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(&ctr[1], 1u);
+        if (prev == gridDim.x - 1) { ctr[1] = 0u; ctr[0] = t + 1u; }
+    }
+}
+__global__ void k_set_ctr(uint32_t *ctr, uint32_t t) { ctr[0] = t; ctr[1] = 0u; }
+
 struct VssStepArgs {
     const float2 *actions;   // [N]
     const float *normals;    // [N][2(R-1)] or null
@@ -22,7 +33,8 @@ struct VssStepArgs {
     float *cmds_out;         // [N][R][2] or null
     int auto_reset, max_steps;
     uint64_t seed;
-    uint32_t t, env_offset;
+    uint32_t *ctr;           // [0] world step counter t (Philox counter word 1), [1] CTAs done
+    uint32_t env_offset;
 };
 
 // VSSEnv.step for BS matches per CTA, one lane per match.  ONE launch = commands (agent +
@@ -37,6 +49,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
     const int e0 = blockIdx.x * BS;
     const int e = e0 + tid;
     const int rows = min(BS, S.n - e0);
+    const uint32_t t_now = *A.ctr;
     if (e < S.n) {
         Scene<R> s;
         load_scene<R>(P, S, e, s);
@@ -67,7 +80,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
             const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
 #pragma unroll
             for (int j = 0; j < (NZ + 3) / 4; ++j) {
-                const uint4 u = philox4x32_10(make_uint4(A.env_offset + (uint32_t)e, A.t, RS_STREAM_OU, j), key);
+                const uint4 u = philox4x32_10(make_uint4(A.env_offset + (uint32_t)e, t_now, RS_STREAM_OU, j), key);
                 float sn, cs;
                 float rr = sqrtf(-2.0f * logf(u01(u.x)));
                 __sincosf(2.0f * RS_PI_F * (u01(u.y) - 0.5f), &sn, &cs);   // angle - pi: flip signs
@@ -121,7 +134,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 
         if (A.auto_reset && (goal || tr)) {                         // rare: stays out of the hot registers
             Scene<0> tmp;
-            vss_place<0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, A.t, RS_STREAM_AUTORESET), tmp);
+            vss_place<0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, t_now, RS_STREAM_AUTORESET), tmp);
             s.bx = tmp.bx; s.by = tmp.by; s.bvx = 0.0f; s.bvy = 0.0f;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -138,6 +151,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         vss_obs<NB, NY>(P, s, tile + tid * NOBS);
     }
     tile_store(A.obs + (size_t)e0 * NOBS, tile, rows, NOBS);
+    bump_step_counter(A.ctr, t_now);
 }
 
 struct SslStepArgs {
@@ -147,7 +161,8 @@ struct SslStepArgs {
     float *cmds_out;         // [N][R][8] or null
     int auto_reset, max_steps;
     uint64_t seed;
-    uint32_t t, env_offset;
+    uint32_t *ctr;
+    uint32_t env_offset;
 };
 
 // SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step
@@ -160,6 +175,7 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
     const int e0 = blockIdx.x * BS;
     const int e = e0 + tid;
     const int rows = min(BS, S.n - e0);
+    const uint32_t t_now = *A.ctr;
     if (e < S.n) {
         Scene<R> s;
         load_scene<R>(P, S, e, s);
@@ -238,7 +254,7 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         for (int i = 0; i < RS_SSL_INFO; ++i) S.info[(size_t)i * S.np + e] = info[i];
         if (A.auto_reset && (dn || tr)) {
             Scene<0> tmp;
-            task_place<TASK, 0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, A.t, RS_STREAM_AUTORESET), tmp);
+            task_place<TASK, 0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, t_now, RS_STREAM_AUTORESET), tmp);
             s.bx = tmp.bx; s.by = tmp.by; s.bvx = 0.0f; s.bvy = 0.0f;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -252,6 +268,7 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         ssl_obs<NB, NY>(P, s, tile + tid * NOBS);
     }
     tile_store(A.obs + (size_t)e0 * NOBS, tile, rows, NOBS);
+    bump_step_counter(A.ctr, t_now);
 }
 
 // simulator.step(cmds): physics only, any (kind, R).  RT > 0: register resident scene.
@@ -377,8 +394,9 @@ __global__ void k_get_raw(const DevParams P, const StatePtrs S, float *__restric
 // env.reset(): initial frame on device + first observation
 template <int TASK>
 __global__ void k_task_reset(const DevParams P, const StatePtrs S, const uint8_t *__restrict__ mask,
-                             float *__restrict__ obs, int obs_dim, uint64_t seed, uint32_t t,
-                             uint32_t env_offset) {
+                             float *__restrict__ obs, int obs_dim, uint64_t seed,
+                             const uint32_t *__restrict__ ctr, uint32_t env_offset) {
+    const uint32_t t = *ctr;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= S.n) return;
     if (mask && !mask[e]) return;
@@ -432,7 +450,9 @@ struct rs_world {
     int n, np, device;
     uint64_t seed;
     int64_t env_offset;
-    uint64_t t;
+    uint64_t t;              // host mirror of d_ctr[0]
+    bool t_dirty;            // host t changed without the device counter (rs_step, rs_set_t)
+    uint32_t *d_ctr;         // device: [0] t, [1] CTAs done (library-owned scratch)
     uint64_t launches;
     void *state;
     int64_t off[RS_ARR_COUNT];
@@ -542,6 +562,10 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     w->state_bytes = o;
     w->block = 64;
     if (const char *bs = getenv("RS_BLOCK")) { const int b = atoi(bs); if (b == 32 || b == 64 || b == 128 || b == 256) w->block = b; }
+    if (cudaMalloc(&w->d_ctr, 2 * sizeof(uint32_t)) != cudaSuccess || cudaMemset(w->d_ctr, 0, 2 * sizeof(uint32_t)) != cudaSuccess) {
+        delete w;
+        return fail(RS_E_CUDA, "rs_create: cudaMalloc of the step counter failed");
+    }
     *out = w;
     return RS_OK;
 }
@@ -549,6 +573,7 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
 int rs_destroy(rs_world *w) {
     if (!w) return RS_OK;
     cudaFree(w->s_actions); cudaFree(w->s_obs); cudaFree(w->s_reward); cudaFree(w->s_done); cudaFree(w->s_trunc);
+    cudaFree(w->d_ctr);
     delete w;
     return RS_OK;
 }
@@ -611,7 +636,7 @@ int rs_step(rs_world *w, const float *d_cmds, void *stream) {
         else if (R == 1) launch_step<RS_KIND_SSL, 1>(w, d_cmds, st);
         else launch_step<RS_KIND_SSL, 0>(w, d_cmds, st);
     }
-    w->launches++; w->t++;
+    w->launches++; w->t++; w->t_dirty = true;
     CUDA_TRY(cudaGetLastError());
     return RS_OK;
 }
@@ -645,10 +670,25 @@ int rs_get_raw(const rs_world *w, float *d_out, void *stream) {
 uint64_t rs_get_t(const rs_world *w) { return w ? w->t : 0; }
 int rs_set_t(rs_world *w, uint64_t t) {
     if (!w) return fail(RS_E_INVALID, "rs_set_t: null world");
+    w->t = t; w->t_dirty = true;
+    return RS_OK;
+}
+int rs_sync_t(rs_world *w, void *stream) {
+    if (!w) return fail(RS_E_INVALID, "rs_sync_t: null world");
+    if (w->t_dirty) return RS_OK;      // host value is the newer one
+    uint32_t t = 0;
+    CUDA_TRY(cudaMemcpyAsync(&t, w->d_ctr, sizeof(t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     w->t = t;
     return RS_OK;
 }
 uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches : 0; }
+
+static void push_t(rs_world *w, cudaStream_t st) {
+    if (!w->t_dirty) return;
+    k_set_ctr<<<1, 1, 0, st>>>(w->d_ctr, (uint32_t)w->t);
+    w->launches++; w->t_dirty = false;
+}
 
 static bool task_matches(const rs_world *w, int task) {
     const rs_params &p = w->p;
@@ -671,7 +711,9 @@ int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, vo
     if (!task_matches(w, task)) return fail(RS_E_UNSUPPORTED, "rs_task_reset: task does not match this world");
     cudaStream_t st = (cudaStream_t)stream;
     const int g = (w->n + 127) / 128, od = rs_task_obs_dim(w, task);
-    const uint32_t t = (uint32_t)w->t, off = (uint32_t)w->env_offset;
+    const uint32_t off = (uint32_t)w->env_offset;
+    push_t(w, st);
+    const uint32_t *t = w->d_ctr;
     if (task == RS_TASK_VSS_V0) k_task_reset<RS_TASK_VSS><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
     else if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) k_task_reset<RS_TASK_SSL_STATIC_DEFENDERS><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
     else k_task_reset<RS_TASK_SSL_CONTESTED_POSSESSION><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
@@ -693,8 +735,9 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
     A.actions = reinterpret_cast<const float2 *>(d_actions); A.normals = d_normals;
     A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.trunc = d_trunc; A.cmds_out = d_cmds_out;
     A.auto_reset = auto_reset; A.max_steps = max_steps;
-    A.seed = w->seed; A.t = (uint32_t)w->t; A.env_offset = (uint32_t)w->env_offset;
     cudaStream_t st = (cudaStream_t)stream;
+    push_t(w, st);
+    A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
     switch (w->block) {
         case 32: k_vss_env_step<3, 3, 32><<<(w->n + 31) / 32, 32, 0, st>>>(w->dp, S, A); break;
@@ -719,8 +762,9 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
     SslStepArgs A;
     A.actions = d_actions; A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.trunc = d_trunc;
     A.cmds_out = d_cmds_out; A.auto_reset = auto_reset; A.max_steps = max_steps;
-    A.seed = w->seed; A.t = (uint32_t)w->t; A.env_offset = (uint32_t)w->env_offset;
     cudaStream_t st = (cudaStream_t)stream;
+    push_t(w, st);
+    A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
     if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {

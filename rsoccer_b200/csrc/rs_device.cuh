@@ -104,43 +104,76 @@ __device__ __forceinline__ bool touching(const DevParams &P, float rx, float ry,
     return touching_local(P, c * dx + s * dy, -s * dx + c * dy);
 }
 
-// walls for one body, mirrored quadrant
+// walls for one body, mirrored quadrant.
+//
+// In steady state ~8 % of the robots touch a wall at any time, so in a warp of 32 matches
+// "some lane touches a wall" is true for almost every body and sub-step: a branchy wall
+// routine runs at 2-4 active lanes and was > 50 % of all issued instructions (profiles/
+// r1_steady_before_walls.txt).  The VSS region (field + goal recesses = rectangle minus one
+// unbounded corner box per quadrant) therefore uses a branch-free form: the faces of the
+// corner box are axis limits selected by where the centre is, only the rounded goal-post
+// corner (both coordinates within r of the box corner) takes a branch.  Same arithmetic
+// as the generic closest-point test of the oracle for every reachable state (and for the
+// unreachable "centre inside the solid" state, which it resolves with the same
+// least-penetration face).
+template <int KIND>
 __device__ __forceinline__ void walls(const DevParams &P, float r, float e, float &x, float &y,
                                       float &vx, float &vy) {
     float ax = fabsf(x), ay = fabsf(y);
-    if (ax + r <= P.x_near && ay <= P.y_out - r) return;   // interior: nothing to do
     const float sx = x < 0.0f ? -1.0f : 1.0f, sy = y < 0.0f ? -1.0f : 1.0f;
     float avx = sx * vx, avy = sy * vy;
-    if (ax + r > P.x_near) {
+    if (KIND == RS_KIND_VSS) {
+        const float Lh = P.box[0][0], Gh = P.box[0][1];
+        const bool inx = ax < Lh, iny = ay < Gh;
+        const float dx = ax - Lh, dy = ay - Gh;
+        if (inx && iny && dx > -r && dy > -r) {          // goal-post corner (rare)
+            const float d2 = dx * dx + dy * dy;
+            if (d2 < r * r) {
+                float nx = -1.0f, ny = 0.0f, pen = r;     // d2 <= 1e-12: oracle's interior rule, m = fxl = 0
+                if (d2 > 1e-12f) { const float inv = rsqrtf(d2); nx = dx * inv; ny = dy * inv; pen = r - d2 * inv; }
+                ax += pen * nx; ay += pen * ny;
+                const float vn = avx * nx + avy * ny;
+                if (vn < 0.0f) { avx -= (1.0f + e) * vn * nx; avy -= (1.0f + e) * vn * ny; }
+            }
+        }
+        const bool interior = !inx && !iny, pick_y = dy < dx;
+        const bool box_x = !iny && !(interior && pick_y);
+        const bool box_y = !inx && !(interior && !pick_y);
+        const float xlim = (box_x ? Lh : P.x_out) - r, ylim = (box_y ? Gh : P.y_out) - r;
+        if (ax > xlim) { ax = xlim; avx = avx > 0.0f ? -e * avx : avx; }
+        if (ay > ylim) { ay = ylim; avy = avy > 0.0f ? -e * avy : avy; }
+    } else {
+        if (ax + r > P.x_near) {                          // near a goal: finite solid boxes
 #pragma unroll
-        for (int k = 0; k < RS_MAX_BOXES; ++k) {
-            if (k < P.n_box) {
-                const float lox = P.box[k][0], loy = P.box[k][1], hix = P.box[k][2], hiy = P.box[k][3];
-                const float qx = clampf(ax, lox, hix), qy = clampf(ay, loy, hiy);
-                const float dx = ax - qx, dy = ay - qy;
-                const float d2 = dx * dx + dy * dy;
-                if (d2 < r * r) {
-                    float nx, ny, pen;
-                    if (d2 > 1e-12f) {
-                        const float inv = rsqrtf(d2);
-                        nx = dx * inv; ny = dy * inv; pen = r - d2 * inv;
-                    } else {
-                        const float fxl = ax - lox, fxh = hix - ax, fyl = ay - loy, fyh = hiy - ay;
-                        float m = fxl; nx = -1.0f; ny = 0.0f;
-                        if (fxh < m) { m = fxh; nx = 1.0f; ny = 0.0f; }
-                        if (fyl < m) { m = fyl; nx = 0.0f; ny = -1.0f; }
-                        if (fyh < m) { m = fyh; nx = 0.0f; ny = 1.0f; }
-                        pen = r + m;
+            for (int k = 0; k < RS_MAX_BOXES; ++k) {
+                if (k < P.n_box) {
+                    const float lox = P.box[k][0], loy = P.box[k][1], hix = P.box[k][2], hiy = P.box[k][3];
+                    const float qx = clampf(ax, lox, hix), qy = clampf(ay, loy, hiy);
+                    const float dx = ax - qx, dy = ay - qy;
+                    const float d2 = dx * dx + dy * dy;
+                    if (d2 < r * r) {
+                        float nx, ny, pen;
+                        if (d2 > 1e-12f) {
+                            const float inv = rsqrtf(d2);
+                            nx = dx * inv; ny = dy * inv; pen = r - d2 * inv;
+                        } else {
+                            const float fxl = ax - lox, fxh = hix - ax, fyl = ay - loy, fyh = hiy - ay;
+                            float m = fxl; nx = -1.0f; ny = 0.0f;
+                            if (fxh < m) { m = fxh; nx = 1.0f; ny = 0.0f; }
+                            if (fyl < m) { m = fyl; nx = 0.0f; ny = -1.0f; }
+                            if (fyh < m) { m = fyh; nx = 0.0f; ny = 1.0f; }
+                            pen = r + m;
+                        }
+                        ax += pen * nx; ay += pen * ny;
+                        const float vn = avx * nx + avy * ny;
+                        if (vn < 0.0f) { avx -= (1.0f + e) * vn * nx; avy -= (1.0f + e) * vn * ny; }
                     }
-                    ax += pen * nx; ay += pen * ny;
-                    const float vn = avx * nx + avy * ny;
-                    if (vn < 0.0f) { avx -= (1.0f + e) * vn * nx; avy -= (1.0f + e) * vn * ny; }
                 }
             }
         }
+        if (ax > P.x_out - r) { ax = P.x_out - r; avx = avx > 0.0f ? -e * avx : avx; }
+        if (ay > P.y_out - r) { ay = P.y_out - r; avy = avy > 0.0f ? -e * avy : avy; }
     }
-    if (ax > P.x_out - r) { ax = P.x_out - r; if (avx > 0.0f) avx = -e * avx; }
-    if (ay > P.y_out - r) { ay = P.y_out - r; if (avy > 0.0f) avy = -e * avy; }
     x = sx * ax; y = sy * ay; vx = sx * avx; vy = sy * avy;
 }
 
@@ -348,9 +381,9 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
             }
         }
         // (f) walls
-        walls(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
+        walls<KIND>(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
 #pragma unroll
-        for (int r = 0; r < R; ++r) walls(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
+        for (int r = 0; r < R; ++r) walls<KIND>(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
     }
 }
 

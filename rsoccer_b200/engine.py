@@ -99,6 +99,11 @@ class BatchedWorld:
     def t(self, v):
         self.L.rs_set_t(self.h, int(v))
 
+    def sync_t(self):
+        """Read the device-resident step counter back (needed after CUDA-graph replays)."""
+        _lib.check(self.L.rs_sync_t(self.h, self._stream()), "rs_sync_t")
+        return self.t
+
     @property
     def launches(self):
         return int(self.L.rs_launch_count(self.h))
