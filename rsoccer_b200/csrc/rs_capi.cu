@@ -13,15 +13,6 @@
 
 // ============================================================================ kernels
 
-// The world step counter lives in device memory so that a captured CUDA graph replays
-// with fresh Philox counters: every CTA reads ctr[0] on entry, the last CTA to finish
-// bumps it (all CTAs have read it by then; the next launch is stream ordered).
-__device__ __forceinline__ void bump_step_counter(uint32_t *ctr, uint32_t t) {
-    if (threadIdx.x == 0) {
-        const uint32_t prev = atomicAdd(&ctr[1], 1u);
-        if (prev == gridDim.x - 1) { ctr[1] = 0u; ctr[0] = t + 1u; }
-    }
-}
 __global__ void k_set_ctr(uint32_t *ctr, uint32_t t) { ctr[0] = t; ctr[1] = 0u; }
 
 struct VssStepArgs {
@@ -41,36 +32,33 @@ struct VssStepArgs {
 // OU noise), 5 physics sub-steps, reward/done/truncation, info accumulators, masked
 // auto-reset and the observation tile (leaves through a TMA bulk store).
 template <int NB, int NY, int BS>
-__global__ void __launch_bounds__(BS)
+__global__ void __launch_bounds__(BS, (448 / BS) > 0 ? (448 / BS) : 1)
 k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
     constexpr int R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
     __shared__ __align__(128) float tile[BS * NOBS];
+    __shared__ uint32_t s_t;
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * BS;
     const int e = e0 + tid;
-    const int rows = min(BS, S.n - e0);
-    const uint32_t t_now = *A.ctr;
+    const int w0 = e0 + (tid & ~31);                       // first env of this warp
+    const int wrows = min(32, S.n - w0);
+    const uint32_t t_now = read_and_bump_step_counter(A.ctr, &s_t);
     if (e < S.n) {
+        // ---- every global load of the step is issued first ...
         Scene<R> s;
         load_scene<R>(P, S, e, s);
         const int st = S.steps[e];
-        int steps = st & 0xFFFFFF;
-        bool has_prev = (st >> 24) & 1;
         float prev = S.prev[e];
         float info[RS_VSS_INFO];
 #pragma unroll
-        for (int i = 0; i < RS_VSS_INFO; ++i) info[i] = steps == 0 ? 0.0f : S.info[(size_t)i * S.np + e];
-        steps += 1;                                                 // vss_gym_base.py:73
-
-        // ---- _get_commands, vss_gym.py:119-142
-        Drive<R> d;
-        d.drib = 0;
+        for (int i = 0; i < RS_VSS_INFO; ++i) info[i] = S.info[(size_t)i * S.np + e];
+        float2 ou[R - 1];
+#pragma unroll
+        for (int r = 1; r < R; ++r) ou[r - 1] = S.ou[(size_t)(r - 1) * S.np + e];
         const float2 act = A.actions[e];
-        float wl0, wr0;
-        vss_action_to_wheels(P, act.x, act.y, wl0, wr0);
-        vss_target(P, wl0, wr0, d.tf[0], d.tw[0]);
-        d.tl[0] = 0.0f; d.kick[0] = 0.0f;
-        if (A.cmds_out) { A.cmds_out[(size_t)e * R * 2] = wl0; A.cmds_out[(size_t)e * R * 2 + 1] = wr0; }
+
+        // ---- ... and the OU noise (Philox + Box-Muller, ~15 % of the instructions, needs
+        // only the env id and the step counter) is computed while they are in flight
         float z[NZ];
         if (A.normals) {
 #pragma unroll
@@ -92,15 +80,32 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
                 if (4 * j + 3 < NZ) z[4 * j + 3] = -rr * sn;
             }
         }
+
+        int steps = st & 0xFFFFFF;
+        bool has_prev = (st >> 24) & 1;
+        if (steps == 0) {
+#pragma unroll
+            for (int i = 0; i < RS_VSS_INFO; ++i) info[i] = 0.0f;
+        }
+        steps += 1;                                                 // vss_gym_base.py:73
+
+        // ---- _get_commands, vss_gym.py:119-142
+        Drive<R> d;
+        d.drib = 0;
+        float wl0, wr0;
+        vss_action_to_wheels(P, act.x, act.y, wl0, wr0);
+        vss_target(P, wl0, wr0, d.tf[0], d.tw[0]);
+        d.tl[0] = 0.0f; d.kick[0] = 0.0f;
+        if (A.cmds_out) { A.cmds_out[(size_t)e * R * 2] = wl0; A.cmds_out[(size_t)e * R * 2 + 1] = wr0; }
 #pragma unroll
         for (int r = 1; r < R; ++r) {
             // Utils/Utils.py:14-21 OU sample (mu = 0, sigma = 0.5, theta = 0.17)
-            float2 ou = S.ou[(size_t)(r - 1) * S.np + e];
-            ou.x = ou.x + (float)RS_OU_THETA * (0.0f - ou.x) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z[2 * (r - 1)];
-            ou.y = ou.y + (float)RS_OU_THETA * (0.0f - ou.y) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z[2 * (r - 1) + 1];
-            S.ou[(size_t)(r - 1) * S.np + e] = ou;
+            float2 o = ou[r - 1];
+            o.x = o.x + (float)RS_OU_THETA * (0.0f - o.x) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z[2 * (r - 1)];
+            o.y = o.y + (float)RS_OU_THETA * (0.0f - o.y) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z[2 * (r - 1) + 1];
+            S.ou[(size_t)(r - 1) * S.np + e] = o;
             float wl, wr;
-            vss_action_to_wheels(P, ou.x, ou.y, wl, wr);
+            vss_action_to_wheels(P, o.x, o.y, wl, wr);
             vss_target(P, wl, wr, d.tf[r], d.tw[r]);
             d.tl[r] = 0.0f; d.kick[r] = 0.0f;
             if (A.cmds_out) { A.cmds_out[((size_t)e * R + r) * 2] = wl; A.cmds_out[((size_t)e * R + r) * 2 + 1] = wr; }
@@ -150,8 +155,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         S.prev[e] = prev;
         vss_obs<NB, NY>(P, s, tile + tid * NOBS);
     }
-    tile_store(A.obs + (size_t)e0 * NOBS, tile, rows, NOBS);
-    bump_step_counter(A.ctr, t_now);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS);
 }
 
 struct SslStepArgs {
@@ -171,11 +175,13 @@ __global__ void __launch_bounds__(BS)
 k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
     constexpr int R = NB + NY, NOBS = 4 + 8 * NB + 2 * NY;
     __shared__ __align__(128) float tile[BS * NOBS];
+    __shared__ uint32_t s_t;
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * BS;
     const int e = e0 + tid;
-    const int rows = min(BS, S.n - e0);
-    const uint32_t t_now = *A.ctr;
+    const int w0 = e0 + (tid & ~31);                       // first env of this warp
+    const int wrows = min(32, S.n - w0);
+    const uint32_t t_now = read_and_bump_step_counter(A.ctr, &s_t);
     if (e < S.n) {
         Scene<R> s;
         load_scene<R>(P, S, e, s);
@@ -267,8 +273,7 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         S.steps[e] = steps;
         ssl_obs<NB, NY>(P, s, tile + tid * NOBS);
     }
-    tile_store(A.obs + (size_t)e0 * NOBS, tile, rows, NOBS);
-    bump_step_counter(A.ctr, t_now);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS);
 }
 
 // simulator.step(cmds): physics only, any (kind, R).  RT > 0: register resident scene.
