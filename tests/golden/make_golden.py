@@ -1,0 +1,185 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference classes.
+
+    python tests/golden/make_golden.py            (needs /root/reference; CPU only)
+
+What is pinned: the reference's own Python task logic -- command conversion
+(vss_gym.py:119-142, 235-254; static_defenders.py:114-148), observation
+(vss_gym.py:93-117; static_defenders.py:90-112), reward / done (vss_gym.py:144-192, 256-311;
+static_defenders.py:150-212, 256-322; contested_possession.py:136-208), the OU process
+(Utils/Utils.py:5-24), the adapter's row packing (Simulators/rsim.py:91-102, 128-155) and
+the Frame parser (Entities/Frame.py:17-93) -- executed by importing rsoccer_gym from
+/root/reference with import-level stand-ins for gymnasium / pygame and with `robosim`
+served by the CPU oracle (tests/golden/shims/robosim.py).  What is NOT pinned: the physics
+inside robosim.step (parity unpinned, see oracle/rs_oracle.c header) -- the state rows in
+these files are the oracle's own.
+
+Per step the files hold everything needed to replay the step in isolation: raw state and
+task state BEFORE the step, the agent action, the standard normals the reference drew,
+and the reference's outputs (sent commands, observation, reward, done, state AFTER).
+"""
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("RS_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "shims"))
+
+import robosim as oracle_robosim  # noqa: E402  (tests/golden/shims)
+from rsoccer_b200 import compat  # noqa: E402
+
+compat.install(robosim_module=oracle_robosim, force_shims=True)
+sys.path.insert(0, REF)
+import gymnasium as gym  # noqa: E402  (the stand-in)
+import rsoccer_gym  # noqa: E402,F401  (the reference, unmodified)
+
+DEG = 180.0 / np.pi
+
+
+def raw_of(env):
+    return env.unwrapped.rsim.simulator._w.get_raw()[0].copy()
+
+
+def set_raw(env, raw):
+    env.unwrapped.rsim.simulator._w.set_raw(raw.reshape(1, -1))
+    u = env.unwrapped
+    u.frame = u.rsim.get_frame()
+
+
+class NormalLog:
+    """records every np.random.normal draw the reference makes (OU noise)."""
+
+    def __init__(self):
+        self.orig = np.random.normal
+        self.draws = []
+
+    def __enter__(self):
+        def normal(*a, **k):
+            v = self.orig(*a, **k)
+            self.draws.append(np.array(v, dtype=np.float64).reshape(-1))
+            return v
+        np.random.normal = normal
+        return self
+
+    def __exit__(self, *a):
+        np.random.normal = self.orig
+
+
+def run_vss(seed, steps, scripted):
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env = gym.make("VSS-v0")
+    u = env.unwrapped
+    rec = {k: [] for k in ("raw_before", "ou_before", "prev_pot", "has_prev", "steps_before", "action",
+                           "normals", "cmds", "obs", "reward", "done", "trunc", "state_after", "raw_after")}
+    obs0, _ = env.reset()
+    rec0 = dict(reset_obs=obs0.astype(np.float64), reset_state=np.array(u.rsim.simulator.get_state()))
+    for t in range(steps):
+        if scripted and t % 40 == 20:      # send the ball towards a goal so that `done` fires
+            raw = raw_of(env)
+            side = 1.0 if (t // 40) % 2 == 0 else -1.0
+            raw[0], raw[1], raw[2], raw[3] = side * 0.66, rng.uniform(-0.1, 0.1), side * 1.5, 0.0
+            set_raw(env, raw)
+        rec["raw_before"].append(raw_of(env))
+        rec["ou_before"].append(np.concatenate([np.asarray(u.ou_actions[i].x_prev, dtype=np.float64) for i in range(1, 6)]))
+        rec["prev_pot"].append(0.0 if u.previous_ball_potential is None else float(u.previous_ball_potential))
+        rec["has_prev"].append(0 if u.previous_ball_potential is None else 1)
+        rec["steps_before"].append(u.steps)
+        a = rng.uniform(-1, 1, 2).astype(np.float32)
+        if t % 7 == 3:
+            a[:] = rng.uniform(-0.06, 0.06, 2)       # exercise the deadzone
+        with NormalLog() as log:
+            obs, rew, term, trunc, info = env.step(a)
+        rec["action"].append(a.astype(np.float64))
+        rec["normals"].append(np.concatenate(log.draws))
+        cm = np.zeros((6, 2))
+        for c in u.sent_commands:
+            cm[(3 + c.id) if c.yellow else c.id] = (c.v_wheel0, c.v_wheel1)
+        rec["cmds"].append(cm.reshape(-1))
+        rec["obs"].append(obs.astype(np.float64))
+        rec["reward"].append(float(rew)); rec["done"].append(int(term)); rec["trunc"].append(int(trunc))
+        rec["state_after"].append(np.array(u.rsim.simulator.get_state()))
+        rec["raw_after"].append(raw_of(env))
+        if term or trunc:
+            env.reset()
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(rec0)
+    out["info_keys"] = np.array(list(info.keys()))
+    out["info_last"] = np.array([float(v) for v in info.values()])
+    out["field"] = np.array([getattr(u.field, k) for k in u.field.__dataclass_fields__])
+    out["max_pos_v_w"] = np.array([u.max_pos, u.max_v, u.max_w])
+    return out
+
+
+def run_ssl(env_id, seed, steps, scripted):
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env = gym.make(env_id)
+    u = env.unwrapped
+    R = u.n_robots_blue + u.n_robots_yellow
+    rec = {k: [] for k in ("raw_before", "steps_before", "action", "cmds", "obs", "reward", "done", "trunc",
+                           "state_after", "raw_after")}
+    env.reset()
+    for t in range(steps):
+        if scripted and t % 30 == 10:       # robot right behind the ball, facing the goal
+            raw = raw_of(env)
+            ang = rng.uniform(-0.4, 0.4)
+            raw[4] = raw[0] - 0.2 * np.cos(ang); raw[5] = raw[1] - 0.2 * np.sin(ang); raw[6] = ang
+            raw[7:10] = 0.0
+            set_raw(env, raw)
+        rec["raw_before"].append(raw_of(env))
+        rec["steps_before"].append(u.steps)
+        a = rng.uniform(-1, 1, 5).astype(np.float32)
+        if scripted:
+            raw = raw_of(env)
+            d = raw[0:2] - raw[4:6]
+            a[0:2] = 0.5 * d / (np.linalg.norm(d) + 1e-9)
+            a[2] = 0.0
+            a[4] = 1.0
+            a[3] = 1.0 if t % 30 == 25 else -1.0
+        obs, rew, term, trunc, info = env.step(a)
+        rec["action"].append(a.astype(np.float64))
+        cm = np.zeros((R, 8))
+        for c in u.sent_commands:
+            row = (u.n_robots_blue + c.id) if c.yellow else c.id
+            cm[row] = (c.wheel_speed, c.v_x, c.v_y, c.v_theta, 0.0, c.kick_v_x, c.kick_v_z, c.dribbler)
+        rec["cmds"].append(cm.reshape(-1))
+        rec["obs"].append(obs.astype(np.float64))
+        rec["reward"].append(float(rew)); rec["done"].append(int(term)); rec["trunc"].append(int(trunc))
+        rec["state_after"].append(np.array(u.rsim.simulator.get_state()))
+        rec["raw_after"].append(raw_of(env))
+        if term or trunc:
+            env.reset()
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["field"] = np.array([getattr(u.field, k) for k in u.field.__dataclass_fields__])
+    out["info_keys"] = np.array(list(info.keys()))
+    return out
+
+
+def main():
+    np.savez_compressed(os.path.join(HERE, "vss_v0_random.npz"), **run_vss(11, 260, False))
+    np.savez_compressed(os.path.join(HERE, "vss_v0_goals.npz"), **run_vss(12, 200, True))
+    np.savez_compressed(os.path.join(HERE, "ssl_static_defenders_random.npz"),
+                        **run_ssl("SSLStaticDefenders-v0", 21, 200, False))
+    np.savez_compressed(os.path.join(HERE, "ssl_static_defenders_fetch.npz"),
+                        **run_ssl("SSLStaticDefenders-v0", 22, 240, True))
+    np.savez_compressed(os.path.join(HERE, "ssl_contested_possession_random.npz"),
+                        **run_ssl("SSLContestedPossession-v0", 31, 200, False))
+    np.savez_compressed(os.path.join(HERE, "ssl_contested_possession_fetch.npz"),
+                        **run_ssl("SSLContestedPossession-v0", 32, 240, True))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            d = np.load(os.path.join(HERE, f))
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes; steps", len(d["reward"]),
+                  "dones", int(d["done"].sum()), "truncs", int(d["trunc"].sum()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""Golden fixtures produced by the UNMODIFIED reference task code (tests/golden/make_golden.py)
+replayed step by step through (a) the CPU oracle and (b) the CUDA path (-m gpu).
+
+Pins commands / observation / reward / done / wire state against the reference's own
+Python (vss_gym.py, static_defenders.py, contested_possession.py, rsim.py, Frame.py)."""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = os.path.join(HERE, "golden")
+
+VSS_FILES = ["vss_v0_random.npz", "vss_v0_goals.npz"]
+SSL_FILES = [("ssl_static_defenders_random.npz", 1, 1, 6, 1000), ("ssl_static_defenders_fetch.npz", 1, 1, 6, 1000),
+             ("ssl_contested_possession_random.npz", 2, 1, 1, 1200), ("ssl_contested_possession_fetch.npz", 2, 1, 1, 1200)]
+
+
+def _load(name):
+    return np.load(os.path.join(G, name))
+
+
+def test_field_params_match_reference_field(oracle):
+    """Field(**get_field_params()) round trip recorded from the reference (rsim.py:49-50)."""
+    d = _load("vss_v0_random.npz")
+    w = oracle.OracleWorld(0, 0, 3, 3)
+    assert np.allclose(d["field"], list(w.field_params().values()))
+    # base-env derived normalisers, vss_gym_base.py:52-58
+    mp, mv, mw = d["max_pos_v_w"]
+    assert abs(mp - 0.9) < 1e-12 and abs(mv - 440 / 60 * 2 * np.pi * 0.026) < 1e-12
+    assert abs(mw - np.rad2deg(mv / 0.04)) < 1e-9
+
+
+@pytest.mark.parametrize("name", VSS_FILES)
+def test_oracle_vss_env_step_vs_reference(oracle, name):
+    d = _load(name)
+    T = len(d["reward"])
+    w = oracle.OracleWorld(0, 0, 3, 3, 25, T)       # one env per recorded step, all replayed at once
+    w.set_raw(d["raw_before"])
+    w.set_task_state(ou=d["ou_before"], prev_pot=d["prev_pot"], has_prev=d["has_prev"],
+                     steps=d["steps_before"], info=np.zeros((T, 9)))
+    obs, rew, done, trunc, cmds = w.vss_env_step(d["action"].astype(np.float32), normals=d["normals"],
+                                                 auto_reset=False, max_steps=1200, want_cmds=True)
+    assert np.abs(cmds.reshape(T, -1) - d["cmds"]).max() < 2e-5        # rad/s; reference path is fp32 for the agent
+    assert (done == d["done"]).all()
+    assert np.abs(w.get_state() - d["state_after"]).max() < 1e-3      # 1e-3: deg/s columns after fp32-vs-fp64 commands
+    assert np.abs(w.get_raw() - d["raw_after"]).max() < 5e-6         # the reference converts the agent action in fp32
+    assert np.abs(obs - d["obs"]).max() < 2e-6                         # reference casts obs to float32
+    assert np.abs(rew - d["reward"]).max() < 1e-6
+    assert d["done"].sum() >= (4 if "goals" in name else 0)
+
+
+@pytest.mark.parametrize("name,task,nb,ny,max_steps", SSL_FILES)
+def test_oracle_ssl_env_step_vs_reference(oracle, name, task, nb, ny, max_steps):
+    d = _load(name)
+    T = len(d["reward"])
+    R = nb + ny
+    w = oracle.OracleWorld(1, 2, nb, ny, 25, T)
+    w.set_raw(d["raw_before"])
+    w.set_task_state(steps=d["steps_before"], info=np.zeros((T, 9)))
+    obs, rew, done, trunc, cmds = w.ssl_env_step(task, d["action"].astype(np.float32), auto_reset=False,
+                                                 max_steps=max_steps, want_cmds=True)
+    assert np.abs(cmds.reshape(T, -1) - d["cmds"]).max() < 1e-6
+    assert (done == d["done"]).all()
+    assert np.abs(w.get_state() - d["state_after"]).max() < 1e-4      # deg/s and wheel rad/s columns; fp32 action path in the reference
+    assert np.abs(obs - d["obs"]).max() < 2e-6
+    assert np.abs(rew - d["reward"]).max() < 1e-6
+    if "fetch" in name:
+        assert d["done"].sum() >= 3 and (d["obs"][:, 11] > 0.5).sum() > 5     # infrared seen
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", VSS_FILES)
+def test_cuda_vss_env_step_vs_reference(engine, name):
+    import torch
+    d = _load(name)
+    T = len(d["reward"])
+    g = engine.BatchedWorld(0, 0, 3, 3, 25, T)
+    g.set_raw(d["raw_before"].astype(np.float32))
+    g.ou[:, :T, :] = torch.tensor(d["ou_before"].reshape(T, 5, 2), dtype=torch.float32).permute(1, 0, 2).cuda()
+    g.prev_pot[:T] = torch.tensor(d["prev_pot"], dtype=torch.float32).cuda()
+    g.steps[:T] = torch.tensor(d["steps_before"] | (d["has_prev"] << 24), dtype=torch.int32).cuda()
+    cg = torch.zeros(T, 6, 2, device="cuda")
+    obs, rew, done, trunc = g.vss_env_step(d["action"].astype(np.float32), normals=d["normals"].astype(np.float32),
+                                           auto_reset=False, max_steps=1200, cmds_out=cg)
+    assert np.abs(cg.cpu().numpy().reshape(T, -1) - d["cmds"]).max() < 1e-4
+    assert (done.cpu().numpy() == d["done"]).all()
+    assert np.abs(obs.cpu().numpy() - d["obs"]).max() < 1e-4
+    assert np.abs(rew.cpu().numpy() - d["reward"]).max() < 2e-4
+    st = g.get_state().cpu().numpy()
+    err = np.abs(st - d["state_after"])
+    for r in range(6):
+        err[:, 5 + 6 * r + 2] = np.abs((st[:, 5 + 6 * r + 2] - d["state_after"][:, 5 + 6 * r + 2] + 180) % 360 - 180)
+        err[:, 5 + 6 * r + 2] /= 100.0     # degrees: 1e-4 rad = 5.7e-3 deg
+        err[:, 5 + 6 * r + 5] /= 100.0
+    assert err.max() < 1e-4, err.max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,task,nb,ny,max_steps", SSL_FILES)
+def test_cuda_ssl_env_step_vs_reference(engine, name, task, nb, ny, max_steps):
+    import torch
+    d = _load(name)
+    T = len(d["reward"])
+    R = nb + ny
+    g = engine.BatchedWorld(1, 2, nb, ny, 25, T)
+    g.set_raw(d["raw_before"].astype(np.float32))
+    g.steps[:T] = torch.tensor(d["steps_before"], dtype=torch.int32).cuda()
+    cg = torch.zeros(T, R, 8, device="cuda")
+    obs, rew, done, trunc = g.ssl_env_step(task, d["action"].astype(np.float32), auto_reset=False,
+                                           max_steps=max_steps, cmds_out=cg)
+    assert np.abs(cg.cpu().numpy().reshape(T, -1) - d["cmds"]).max() < 1e-4
+    # a recorded frame may sit within fp32 rounding of a decision boundary; allow <= 1 flip
+    assert (done.cpu().numpy() != d["done"]).sum() <= 1
+    ok = done.cpu().numpy() == d["done"]
+    eo = np.abs(obs.cpu().numpy() - d["obs"]).max(axis=1)
+    er = np.abs(rew.cpu().numpy() - d["reward"])
+    assert (eo[ok] < 3e-4).mean() > 0.99 and np.median(eo) < 1e-5
+    assert (er[ok] < 3e-4).mean() > 0.99
