@@ -43,12 +43,14 @@ class Env:
         return self
 
 
-class Wrapper(Env):
+class Wrapper:
+    """forwards everything it does not define to the wrapped env (spaces, metadata, hooks)"""
+
     def __init__(self, env):
         self.env = env
 
     def __getattr__(self, name):
-        if name.startswith("_"):
+        if name.startswith("_") or name == "env":
             raise AttributeError(name)
         return getattr(self.env, name)
 

@@ -1,0 +1,131 @@
+"""The three benchmarked reference envs as batched envs whose `step` is ONE fused launch.
+
+    VSSVecEnv                       <- rsoccer_gym/vss/env_vss/vss_gym.py           (VSS-v0)
+    SSLStaticDefendersVecEnv        <- ssl/ssl_hw_challenge/static_defenders.py     (SSLStaticDefenders-v0)
+    SSLContestedPossessionVecEnv    <- ssl/ssl_hw_challenge/contested_possession.py (SSLContestedPossession-v0)
+
+API (gymnasium VectorEnv flavour, same-step auto-reset):
+    obs, info = env.reset()
+    obs, reward, terminated, truncated, info = env.step(actions)     # torch CUDA tensors, [N, ...]
+`info` is the reference's `reward_shaping_total` dict (vss_gym.py:150-158) with one [N] tensor
+per key (zero-copy views of the on-device accumulators).  When an episode ends the returned
+observation is the first one of the next episode; `truncated` follows the registered step
+limits (rsoccer_gym/__init__.py:3-30).
+"""
+import torch
+
+from .. import engine as _E
+from ..entities import FrameSSL, FrameVSS
+from .base import BoxSpec
+
+VSS_INFO_KEYS = ("goal_score", "move", "ball_grad", "energy", "goals_blue", "goals_yellow")
+SSL_INFO_KEYS = ("goal", "rbt_in_gk_area", "done_ball_out", "done_ball_out_right", "done_rbt_out",
+                 "ball_dist", "ball_grad", "energy", "collision")
+
+
+class _FusedVecEnv:
+    KIND = None
+    TASK = None
+    FIELD_TYPE = None
+    N_BLUE = N_YELLOW = None
+    ACT_DIM = None
+    MAX_EPISODE_STEPS = None
+    INFO_KEYS = ()
+    NORM_BOUNDS = 1.2
+
+    def __init__(self, num_envs=1, device=None, seed=0, env_offset=0, auto_reset=True, max_episode_steps=None,
+                 field_type=None, render_mode=None):
+        if render_mode is not None:
+            raise NotImplementedError("rendering is out of scope of rsoccer_b200")
+        self.num_envs = int(num_envs)
+        self.auto_reset = bool(auto_reset)
+        self.max_episode_steps = int(max_episode_steps or self.MAX_EPISODE_STEPS)
+        self.time_step = 0.025
+        ft = self.FIELD_TYPE if field_type is None else field_type
+        self.world = _E.BatchedWorld(self.KIND, ft, self.N_BLUE, self.N_YELLOW, 25, self.num_envs, device=device,
+                                     seed=seed, env_offset=env_offset)
+        self.device = self.world.device
+        self.n_robots_blue, self.n_robots_yellow = self.N_BLUE, self.N_YELLOW
+        self.obs_dim = self.world.obs_dim(self.TASK)
+        self.action_space = BoxSpec(-1.0, 1.0, (self.num_envs, self.ACT_DIM))
+        self.observation_space = BoxSpec(-self.NORM_BOUNDS, self.NORM_BOUNDS, (self.num_envs, self.obs_dim))
+        self._out = self.world.alloc_outputs(self.TASK)
+        self._pinned = None
+        self.field = None
+
+    # ---- gym surface
+    def reset(self, *, seed=None, options=None, mask=None):
+        obs = self.world.task_reset(self.TASK, mask=mask, obs=self._out[0] if mask is None else None)
+        return obs, self.info()
+
+    def step(self, actions):
+        obs, rew, done, trunc = self._step(actions)
+        return obs, rew, done.bool(), trunc.bool(), self.info()
+
+    def step_raw(self, actions):
+        """step without building the info dict / bool casts: (obs, reward, done u8, trunc u8)"""
+        return self._step(actions)
+
+    def info(self):
+        n = self.num_envs
+        return {k: self.world.info[i, :n] for i, k in enumerate(self.INFO_KEYS)}
+
+    def close(self):
+        self.world.close()
+
+    # ---- host-buffer end-to-end call (numpy in / numpy out through pinned memory)
+    def step_host(self, actions_np):
+        if self._pinned is None:
+            n = self.num_envs
+            self._pinned = (torch.empty(n, self.ACT_DIM, dtype=torch.float32).pin_memory(),
+                            torch.empty(n, self.obs_dim, dtype=torch.float32).pin_memory(),
+                            torch.empty(n, dtype=torch.float32).pin_memory(),
+                            torch.empty(n, dtype=torch.uint8).pin_memory(),
+                            torch.empty(n, dtype=torch.uint8).pin_memory())
+        a, o, r, d, t = self._pinned
+        a.copy_(torch.as_tensor(actions_np, dtype=torch.float32).reshape(a.shape))
+        self._step_host(a, o, r, d, t)
+        return o.numpy(), r.numpy(), d.numpy().astype(bool), t.numpy().astype(bool)
+
+    # ---- batched Frame view of the current state (Entities/Frame.py layout)
+    @property
+    def frame(self):
+        st = self.world.get_state()
+        f = FrameVSS() if self.KIND == _E.KIND_VSS else FrameSSL()
+        return f.parse(st, self.N_BLUE, self.N_YELLOW)
+
+
+class VSSVecEnv(_FusedVecEnv):
+    KIND, TASK, FIELD_TYPE, N_BLUE, N_YELLOW, ACT_DIM = _E.KIND_VSS, _E.TASK_VSS_V0, 0, 3, 3, 2
+    MAX_EPISODE_STEPS = 1200              # rsoccer_gym/__init__.py:4
+    INFO_KEYS = VSS_INFO_KEYS
+
+    def _step(self, actions):
+        return self.world.vss_env_step(actions, auto_reset=self.auto_reset, max_steps=self.max_episode_steps,
+                                       out=self._out)
+
+    def _step_host(self, a, o, r, d, t):
+        self.world.vss_env_step_host(a, o, r, d, t, auto_reset=self.auto_reset, max_steps=self.max_episode_steps)
+
+
+class _SSLFused(_FusedVecEnv):
+    KIND, FIELD_TYPE, ACT_DIM = _E.KIND_SSL, 2, 5
+    INFO_KEYS = SSL_INFO_KEYS
+
+    def _step(self, actions):
+        return self.world.ssl_env_step(self.TASK, actions, auto_reset=self.auto_reset,
+                                       max_steps=self.max_episode_steps, out=self._out)
+
+    def _step_host(self, a, o, r, d, t):
+        self.world.ssl_env_step_host(self.TASK, a, o, r, d, t, auto_reset=self.auto_reset,
+                                     max_steps=self.max_episode_steps)
+
+
+class SSLStaticDefendersVecEnv(_SSLFused):
+    TASK, N_BLUE, N_YELLOW = _E.TASK_SSL_STATIC_DEFENDERS_V0, 1, 6
+    MAX_EPISODE_STEPS = 1000              # rsoccer_gym/__init__.py:11
+
+
+class SSLContestedPossessionVecEnv(_SSLFused):
+    TASK, N_BLUE, N_YELLOW = _E.TASK_SSL_CONTESTED_POSSESSION_V0, 1, 1
+    MAX_EPISODE_STEPS = 1200              # rsoccer_gym/__init__.py:24

@@ -1,0 +1,118 @@
+"""The oracle itself: RNG known answers, conditioning diagnostic, and (when the reference
+tree is present, i.e. in the build container) the unmodified reference envs running on it."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def test_philox_known_answers(oracle):
+    """Random123 kat_vectors, philox4x32-10 (Salmon et al. SC'11)."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, out in kat:
+        assert oracle.philox4x32_10(ctr, key).tolist() == out
+
+
+def test_ou_noise_statistics(oracle):
+    """Box-Muller on the Philox stream gives N(0,1); the OU recursion matches Utils/Utils.py:14-21."""
+    n = 4096
+    w = oracle.OracleWorld(0, 0, 3, 3, 25, n, seed=123)
+    w.task_reset(oracle.TASK_VSS)
+    acts = np.zeros((n, 2), dtype=np.float32)
+    prev = w.get_task_state()["ou"]
+    zs = []
+    for _ in range(20):
+        w.vss_env_step(acts, auto_reset=False)
+        cur = w.get_task_state()["ou"]
+        zs.append((cur - prev - 0.17 * (0.0 - prev) * 0.025) / (0.5 * np.sqrt(0.025)))
+        prev = cur
+    z = np.concatenate(zs).ravel()
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert abs(np.mean(z ** 3)) < 0.03 and abs(np.mean(z ** 4) - 3.0) < 0.1
+    assert np.abs(np.corrcoef(np.concatenate(zs)[:, 0], np.concatenate(zs)[:, 1])[0, 1]) < 0.01
+
+
+def test_reset_placement_respects_reference_constraints(oracle):
+    """vss_gym.py:194-233 (inset 0.1, min distance 0.1), static_defenders.py:214-254 (min 0.2, ball not in
+    the goalkeeper area), contested_possession.py:210-227 (ball 0.1 m in front of the yellow robot)."""
+    n = 2000
+    w = oracle.OracleWorld(0, 0, 3, 3, 25, n, seed=5)
+    w.task_reset(oracle.TASK_VSS)
+    raw = w.get_raw()
+    pos = np.concatenate([raw[:, None, 0:2]] + [raw[:, None, 4 + 6 * r:6 + 6 * r] for r in range(6)], axis=1)
+    assert np.abs(pos[:, :, 0]).max() <= 0.65 and np.abs(pos[:, :, 1]).max() <= 0.55
+    d = np.linalg.norm(pos[:, :, None] - pos[:, None], axis=-1) + np.eye(7) * 9
+    assert d.min() >= 0.1
+    th = raw[:, 6::6]
+    assert th.min() > -np.pi - 1e-9 and th.max() <= np.pi + 1e-9 and th.std() > 1.5
+
+    w = oracle.OracleWorld(1, 2, 1, 6, 25, n, seed=5)
+    f = w.field_params()
+    w.task_reset(oracle.TASK_SSL_STATIC_DEFENDERS)
+    raw = w.get_raw()
+    pos = np.concatenate([raw[:, None, 0:2]] + [raw[:, None, 4 + 6 * r:6 + 6 * r] for r in range(7)], axis=1)
+    assert np.allclose(pos[:, 1], 0.0)
+    assert pos[:, [0, 2, 3, 4, 5, 6, 7], 0].min() >= 0.2
+    d = np.linalg.norm(pos[:, :, None] - pos[:, None], axis=-1) + np.eye(8) * 9
+    assert d.min() >= 0.2 - 1e-12
+    in_gk = (pos[:, 0, 0] > f["length"] / 2 - f["penalty_length"]) & (np.abs(pos[:, 0, 1]) < f["penalty_width"] / 2)
+    assert not in_gk.any()
+
+    w = oracle.OracleWorld(1, 2, 1, 1, 25, n, seed=5)
+    w.task_reset(oracle.TASK_SSL_CONTESTED_POSSESSION)
+    raw = w.get_raw()
+    assert np.allclose(raw[:, 0], raw[:, 10] - 0.1) and np.allclose(raw[:, 1], raw[:, 11])
+    assert np.allclose(np.abs(raw[:, 12]), np.pi)
+    assert w.get_state()[:, 5 + 11 + 6].min() == 1.0         # K7: the yellow robot's infrared sees the ball
+
+
+def test_margin_flags_near_grazing_contacts(oracle):
+    """the conditioning diagnostic used by the parity tests: a contact decided by < 5e-6 m is flagged."""
+    w = oracle.OracleWorld(0, 0, 3, 3, 25, 2)
+    rs = 0.0375 + 0.0215
+    far = [[-0.5, 0.5, 0], [-0.5, -0.5, 0], [0.5, 0.5, 0]]
+    w.reset([[0, 0, 0, 0], [0, 0, 0, 0]], [[[rs + 1e-7, 0, 0]] + far[:2], [[rs + 0.01, 0, 0]] + far[:2]],
+            [[[0.5, -0.5, 0], [0.3, 0.5, 0], [0.3, -0.5, 0]]] * 2)
+    w.step(np.zeros((2, 6, 2)))
+    m = w.margin()
+    assert m[0] < 5e-6 and m[1] > 1e-3
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_unmodified_reference_envs_run_on_the_oracle():
+    """BASELINE config 1: gym.make(...) of the reference package, robosim served by the oracle,
+    gymnasium / pygame by the import-level stand-ins; README.md:116-133 loop."""
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import robosim as R
+from rsoccer_b200 import compat
+compat.install(robosim_module=R, force_shims=True)
+sys.path.insert(0, %r)
+import gymnasium as gym, rsoccer_gym, numpy as np
+for eid, nobs in (("VSS-v0", 40), ("SSLStaticDefenders-v0", 24), ("SSLContestedPossession-v0", 14),
+                  ("SSLDribbling-v0", None), ("SSLPassEndurance-v0", None)):
+    env = gym.make(eid)
+    obs, _ = env.reset()
+    assert obs.shape == env.observation_space.shape and (nobs is None or obs.shape == (nobs,)), (eid, obs.shape)
+    n = 0
+    terminated = truncated = False
+    while not (terminated or truncated) and n < 60:
+        obs, reward, terminated, truncated, info = env.step(env.action_space.sample())
+        n += 1
+    assert np.isfinite(obs).all() and np.abs(obs).max() <= 1.2 + 1e-6, eid
+    env.close()
+print("OK")
+''' % (ROOT, os.path.join(ROOT, "tests", "golden", "shims"), REF)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
