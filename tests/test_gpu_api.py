@@ -1,0 +1,205 @@
+"""-m gpu: the host-side mirrors of the reference interface on top of the CUDA engine."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_robosim_shim_matches_oracle_shim(engine, oracle):
+    """the same call sequence rsim.py makes (ctor, get_field_params, reset, step, get_state) through the
+    CUDA-backed `robosim` module and through the oracle-backed one"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden", "shims"))
+    import robosim as O_sim
+    from rsoccer_b200.compat import robosim as G_sim
+    rng = np.random.default_rng(0)
+    for cls, nb, ny, C, ft in (("VSS", 3, 3, 2, 0), ("SSL", 1, 6, 8, 2)):
+        R = nb + ny
+        ball = [0, 0, 0, 0]
+        blue = [[-0.2 * i, 0, 0] for i in range(1, nb + 1)]          # rsim.py:19-24
+        yel = [[0.2 * i, 0, 0] for i in range(1, ny + 1)]
+        g = getattr(G_sim, cls)(ft, nb, ny, 25, ball, blue, yel)
+        o = getattr(O_sim, cls)(ft, nb, ny, 25, ball, blue, yel)
+        assert g.get_field_params().keys() == o.get_field_params().keys()
+        assert np.allclose(list(g.get_field_params().values()), list(o.get_field_params().values()))
+        b = np.array([0.3, 0.1, -0.5, 0.2])
+        bl = np.column_stack([rng.uniform(-0.6, -0.1, nb), rng.uniform(-0.5, 0.5, nb), rng.uniform(0, 360, nb)])
+        ye = np.column_stack([rng.uniform(0.1, 0.6, ny), np.linspace(-0.5, 0.5, ny), rng.uniform(0, 360, ny)])
+        g.reset(b, bl, ye); o.reset(b, bl, ye)
+        for _ in range(20):
+            cmd = np.zeros((R, C))
+            if C == 2:
+                cmd[:] = rng.uniform(-30, 30, (R, 2))
+            else:
+                cmd[:, 1:4] = rng.uniform(-1, 1, (R, 3))
+            g.step(cmd); o.step(cmd)
+        sg, so = np.asarray(g.get_state()), np.asarray(o.get_state())
+        assert sg.dtype == np.float64 and sg.shape == so.shape == (5 + (6 if C == 2 else 11) * R,)
+        assert np.abs(sg - so).max() < 5e-3       # degrees / wheel rad/s columns dominate
+        K = 6 if C == 2 else 11
+        xy = [0, 1, 3, 4] + [5 + K * r + c for r in range(R) for c in (0, 1, 3, 4)]
+        assert np.abs(sg[xy] - so[xy]).max() < 1e-4
+        with pytest.raises(IndexError):
+            g.step(np.zeros((R + 1, C)))
+
+
+def test_batched_rsim_adapter_reset_send_get(engine):
+    """RSimVSS mirror: reset(frame) / send_commands(List[Robot]) / get_frame() with per-env tensors"""
+    from rsoccer_b200.entities import Ball, Frame, Robot
+    from rsoccer_b200.simulators import RSimVSS
+    n = 16
+    sim = RSimVSS(0, 3, 3, 25, n_envs=n)
+    assert sim.field.length == 1.5 and sim.field.rbt_radius == 0.0375
+    fr = Frame()
+    fr.ball = Ball(x=torch.linspace(-0.3, 0.3, n), y=0.0)
+    for i in range(3):
+        fr.robots_blue[i] = Robot(x=-0.5, y=-0.3 + 0.3 * i, theta=torch.full((n,), 90.0))
+        fr.robots_yellow[i] = Robot(x=0.5, y=-0.3 + 0.3 * i, theta=180.0)
+    sim.reset(fr)
+    f0 = sim.get_frame()
+    assert torch.allclose(f0.ball.x.cpu(), torch.linspace(-0.3, 0.3, n), atol=1e-6)
+    assert torch.allclose(f0.robots_blue[1].theta.cpu(), torch.full((n,), 90.0), atol=1e-3)
+    w = torch.linspace(5, 36, n)
+    for _ in range(10):
+        sim.send_commands([Robot(yellow=True, id=2, v_wheel0=w, v_wheel1=w)])
+    f1 = sim.get_frame()
+    assert torch.allclose(f1.robots_yellow[2].v_x.cpu(), -w * 0.026, atol=1e-4)    # facing 180 deg
+    assert f1.robots_blue[0].v_x.abs().max() < 1e-6                                # K12 zero rows
+    with pytest.raises(IndexError):
+        sim.send_commands([Robot(yellow=False, id=3, v_wheel0=1.0, v_wheel1=1.0)])
+    sim.stop()
+
+
+def test_user_subclass_of_the_batched_base_env(engine):
+    """the reference README's example env (README.md:71-113), written against the batched base class"""
+    from rsoccer_b200.entities import Ball, Frame, Robot
+    from rsoccer_b200.envs import SSLBaseVecEnv
+
+    class Example(SSLBaseVecEnv):
+        def __init__(self, num_envs):
+            super().__init__(field_type=0, n_robots_blue=1, n_robots_yellow=0, time_step=0.025, num_envs=num_envs)
+
+        def _frame_to_observations(self):
+            b, r = self.frame.ball, self.frame.robots_blue[0]
+            return torch.stack([b.x, b.y, r.x, r.y], dim=1)
+
+        def _get_commands(self, actions):
+            return [Robot(yellow=False, id=0, v_x=actions[:, 0], v_y=actions[:, 1])]
+
+        def _calculate_reward_and_done(self):
+            goal = (self.frame.ball.x > self.field.length / 2) & (self.frame.ball.y.abs() < self.field.goal_width / 2)
+            return goal.float(), goal
+
+        def _get_initial_positions_frame(self):
+            f = Frame()
+            f.ball = Ball(x=self.field.length / 2 - self.field.penalty_length, y=0.0)
+            f.robots_blue[0] = Robot(x=0.0, y=0.0, theta=0.0)
+            return f
+
+    env = Example(8)
+    obs, _ = env.reset()
+    assert obs.shape == (8, 4) and torch.allclose(obs[:, 0].cpu(), torch.full((8,), 3.5))
+    a = torch.zeros(8, 2, device=obs.device); a[:, 0] = torch.linspace(0.5, 2.0, 8)
+    for _ in range(40):
+        obs, rew, done, trunc, _ = env.step(a)
+    assert (obs[1:, 2] > obs[:-1, 2]).all() and obs[:, 2].min() > 0.3
+    assert not done.any() and rew.sum() == 0
+    env.close()
+
+
+def test_fused_vec_env_api_and_host_path(engine):
+    from rsoccer_b200 import envs
+    n = 1000                        # not a multiple of 32 or 64: ragged last warp / CTA
+    env = envs.make("VSS-v0", num_envs=n, seed=4)
+    ref = envs.make("VSS-v0", num_envs=n, seed=4)
+    obs, info = env.reset()
+    ref.reset()
+    assert obs.shape == (n, 40) and obs.dtype == torch.float32 and obs.is_cuda
+    assert set(info) == {"goal_score", "move", "ball_grad", "energy", "goals_blue", "goals_yellow"}
+    g = torch.Generator().manual_seed(0)
+    for t in range(30):
+        a = torch.rand(n, 2, generator=g) * 2 - 1
+        o1, r1, d1, t1, i1 = env.step(a.cuda())
+        o2, r2, d2, t2 = ref.step_host(a.numpy())                  # numpy in / numpy out, pinned staging
+        assert o1.abs().max() <= 1.2 + 1e-6 and d1.dtype == torch.bool
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy(), d2) and np.array_equal(t1.cpu().numpy(), t2)
+    assert float(i1["energy"].max()) < 0 and i1["move"].shape == (n,)
+    f = env.frame
+    assert f.ball.x.shape == (n,) and len(f.robots_blue) == 3
+    with pytest.raises(KeyError):
+        envs.make("SSLDribbling-v0")
+    for eid, od in (("SSLStaticDefenders-v0", 24), ("SSLContestedPossession-v0", 14)):
+        e = envs.make(eid, num_envs=70)
+        o, _ = e.reset()
+        assert o.shape == (70, od)
+        o, r, d, tr, i = e.step(torch.zeros(70, 5, device="cuda"))
+        assert o.shape == (70, od) and "collision" in i
+        e.close()
+
+
+def test_time_limit_truncation_and_autoreset(engine):
+    from rsoccer_b200 import envs
+    env = envs.make("VSS-v0", num_envs=64, max_episode_steps=5)
+    env.reset()
+    a = torch.zeros(64, 2, device="cuda")
+    flags = [bool(env.step(a)[3].all()) for _ in range(12)]
+    assert flags == [False] * 4 + [True] + [False] * 4 + [True] + [False] * 2
+    assert int(env.world.steps[:64].max() & 0xFFFFFF) == 2
+    env2 = envs.make("VSS-v0", num_envs=64, max_episode_steps=5, auto_reset=False)
+    env2.reset()
+    tr = [bool(env2.step(a)[3].all()) for _ in range(7)]
+    assert tr == [False] * 4 + [True] * 3
+
+
+def test_cuda_graph_replay_draws_fresh_noise(engine):
+    """the Philox step counter lives in device memory: replays of one captured launch differ"""
+    E = engine
+    n = 256
+    w = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=1)
+    w.task_reset(E.TASK_VSS_V0)
+    a = torch.zeros(n, 2, device="cuda")
+    out = w.alloc_outputs(E.TASK_VSS_V0)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            w.vss_env_step(a, out=out)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            w.vss_env_step(a, out=out)
+        ou = []
+        for _ in range(4):
+            g.replay()
+            s.synchronize()
+            ou.append(w.ou[:, :n].clone())
+    # 3 eager steps + 4 replays ran on the device (the capture itself executes nothing; the
+    # host mirror counted it, which is why rs_sync_t exists)
+    assert w.t == 4 and w.sync_t() == 7
+    inc = [(ou[i + 1] - ou[i] * (1 - 0.17 * 0.025)) for i in range(3)]
+    assert not torch.allclose(inc[0], inc[1]) and not torch.allclose(inc[1], inc[2])
+    # and the replayed steps equal eager steps of a twin world
+    w2 = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=1)
+    w2.task_reset(E.TASK_VSS_V0)
+    for _ in range(7):
+        w2.vss_env_step(a)
+    assert torch.equal(w2.get_raw(), w.get_raw())
+
+
+def test_checkpoint_restore_via_state_tensor(engine):
+    """the state is one torch tensor -> clone/restore is a full checkpoint"""
+    E = engine
+    w = E.BatchedWorld(0, 0, 3, 3, 25, 128, seed=9)
+    w.task_reset(E.TASK_VSS_V0)
+    a = torch.rand(128, 2, device="cuda") * 2 - 1
+    for _ in range(5):
+        w.vss_env_step(a)
+    snap, t = w.state.clone(), w.t
+    ref = [w.vss_env_step(a)[0].clone() for _ in range(5)]
+    w.state.copy_(snap); w.t = t
+    again = [w.vss_env_step(a)[0].clone() for _ in range(5)]
+    assert all(torch.equal(x, y) for x, y in zip(ref, again))
