@@ -102,7 +102,8 @@ def cpu_baseline_run(threads, target_seconds, envs=4096):
     import numpy as np
     from oracle import oracle as O
     O.build()
-    threads = max(1, min(threads, O.max_threads()))
+    # num_threads() in the oracle's omp pragma overrides OMP_NUM_THREADS (torchrun sets it to 1)
+    threads = O.usable_threads(threads)
     w = O.OracleWorld(O.KIND_VSS, 0, 3, 3, 25, envs, seed=1, threads=threads)
     w.task_reset(O.TASK_VSS)
     rng = np.random.default_rng(0)
@@ -129,7 +130,7 @@ def run_reference(args, rank, world):
     import numpy as np
     from oracle import oracle as O
     O.build()
-    threads = O.max_threads()
+    threads = O.usable_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     envs = 8192
     w = O.OracleWorld(O.KIND_VSS, 0, 3, 3, 25, envs, seed=1, threads=threads)
     w.task_reset(O.TASK_VSS)
@@ -293,7 +294,8 @@ def main():
                 traffic = json.load(f).get("k_vss_env_step_dram_bytes_per_launch")
         except Exception:
             pass
-        cpu = cpu_baseline_run(os.cpu_count() or 1, args.cpu_seconds)
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        cpu = cpu_baseline_run(ncpu, args.cpu_seconds)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

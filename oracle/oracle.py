@@ -70,6 +70,7 @@ def lib():
         L.orc_task_obs.argtypes = [vp, i32, vp]
         L.orc_philox.argtypes = [vp, vp, vp]
         L.orc_max_threads.restype = i32
+        L.orc_has_openmp.restype = i32
         _lib = L
     return _lib
 
@@ -88,6 +89,12 @@ def philox4x32_10(ctr, key):
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def usable_threads(want):
+    """threads the oracle can really use: `want` when built with OpenMP (its pragma's num_threads()
+    overrides OMP_NUM_THREADS), else 1"""
+    return max(1, int(want)) if lib().orc_has_openmp() else 1
 
 
 class OracleWorld:

@@ -849,3 +849,11 @@ int orc_max_threads(void) {
     return 1;
 #endif
 }
+
+int orc_has_openmp(void) {
+#ifdef _OPENMP
+    return 1;
+#else
+    return 0;
+#endif
+}
