@@ -10,10 +10,14 @@
 
 #include "../../include/rsoccer_b200.h"
 #include "rs_tasks.cuh"
+#include "rs_lanes.cuh"
 
 // ============================================================================ kernels
 
-__global__ void k_set_ctr(uint32_t *ctr, uint32_t t) { ctr[0] = t; ctr[1] = 0u; }
+__global__ void k_set_ctr(uint32_t *ctr, int n_ctr, uint32_t t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ctr) ctr[i] = t;
+}
 
 struct VssStepArgs {
     const float2 *actions;   // [N]
@@ -24,7 +28,7 @@ struct VssStepArgs {
     float *cmds_out;         // [N][R][2] or null
     int auto_reset, max_steps;
     uint64_t seed;
-    uint32_t *ctr;           // [0] world step counter t (Philox counter word 1), [1] CTAs done
+    uint32_t *ctr;           // world step counter t (Philox counter word 1), one copy per RS_CTR_GROUP matches
     uint32_t env_offset;
 };
 
@@ -36,13 +40,12 @@ __global__ void __launch_bounds__(BS, (448 / BS) > 0 ? (448 / BS) : 1)
 k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
     constexpr int R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
     __shared__ __align__(128) float tile[BS * NOBS];
-    __shared__ uint32_t s_t;
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * BS;
     const int e = e0 + tid;
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
-    const uint32_t t_now = read_and_bump_step_counter(A.ctr, &s_t);
+    const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
     if (e < S.n) {
         // ---- every global load of the step is issued first ...
         Scene<R> s;
@@ -56,6 +59,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 #pragma unroll
         for (int r = 1; r < R; ++r) ou[r - 1] = S.ou[(size_t)(r - 1) * S.np + e];
         const float2 act = A.actions[e];
+        const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
 
         // ---- ... and the OU noise (Philox + Box-Muller, ~15 % of the instructions, needs
         // only the env id and the step counter) is computed while they are in flight
@@ -70,11 +74,11 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
             for (int j = 0; j < (NZ + 3) / 4; ++j) {
                 const uint4 u = philox4x32_10(make_uint4(A.env_offset + (uint32_t)e, t_now, RS_STREAM_OU, j), key);
                 float sn, cs;
-                float rr = sqrtf(-2.0f * logf(u01(u.x)));
+                float rr = sqrtf(-2.0f * __logf(u01(u.x)));
                 __sincosf(2.0f * RS_PI_F * (u01(u.y) - 0.5f), &sn, &cs);   // angle - pi: flip signs
                 if (4 * j < NZ) z[4 * j] = -rr * cs;
                 if (4 * j + 1 < NZ) z[4 * j + 1] = -rr * sn;
-                rr = sqrtf(-2.0f * logf(u01(u.z)));
+                rr = sqrtf(-2.0f * __logf(u01(u.z)));
                 __sincosf(2.0f * RS_PI_F * (u01(u.w) - 0.5f), &sn, &cs);
                 if (4 * j + 2 < NZ) z[4 * j + 2] = -rr * cs;
                 if (4 * j + 3 < NZ) z[4 * j + 3] = -rr * sn;
@@ -112,7 +116,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         }
 
         // ---- rsim.send_commands + get_frame, vss_gym_base.py:77-82
-        physics_step<RS_KIND_VSS, R>(P, s, d);
+        physics_step<RS_KIND_VSS, R>(P, s, d, live);
 
         // ---- _calculate_reward_and_done, vss_gym.py:144-192
         float rew; bool goal = false;
@@ -154,8 +158,150 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         S.steps[e] = steps | ((has_prev ? 1 : 0) << 24);
         S.prev[e] = prev;
         vss_obs<NB, NY>(P, s, tile + tid * NOBS);
+        step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
     }
     warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS);
+}
+
+
+// VSSEnv.step, one lane per BODY (rs_lanes.cuh): 8 lanes per 3 v 3 match, BS / 8 matches per
+// CTA.  Same launch contract as k_vss_env_step.  The eight task words of a match (previous
+// potential, step counter, six reward_shaping_total accumulators) are one word per lane:
+// one load and one store instruction for all of them.
+template <int BS>
+__global__ void __launch_bounds__(BS)
+k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
+    constexpr int L = 8, NB = 3, NY = 3, R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
+    constexpr int EPB = BS / L, MPW = 32 / L;
+    static_assert(RS_AUX_INFO + RS_VSS_INFO == L, "one task word per lane");
+    __shared__ __align__(128) float tile[EPB * NOBS];
+    const int tid = threadIdx.x;
+    const int b = tid & (L - 1);                               // body of this lane
+    const int el = tid / L;                                    // match within the CTA
+    const int e = blockIdx.x * EPB + el;
+    const bool valid = e < S.n;
+    const int ec = valid ? e : S.n - 1;                        // dead groups shadow the last match (no stores)
+    const int w0 = blockIdx.x * EPB + (tid >> 5) * MPW;        // first match of this warp
+    const int wrows = min(MPW, S.n - w0);
+    const LaneGroup<L> g;
+    const bool is_robot = b >= 1 && b <= R, is_ou = b >= 2 && b <= R;
+    const int p = is_ou ? b - 2 : 0;                           // OU process of this lane (blue 0 is the agent)
+    const uint32_t gid = A.env_offset + (uint32_t)ec;
+
+    // ---- loads first: own body, own task word, own action source
+    LaneBody s;
+    lanes_load<L>(S, R, b, ec, s);
+    const uint32_t aux = S.aux[(size_t)b * S.np + ec];
+    float2 a = make_float2(0.0f, 0.0f);
+    if (b == 1) a = A.actions[ec];
+    if (is_ou) a = S.ou[(size_t)p * S.np + ec];
+    const uint32_t t_now = step_counter_read<RS_CTR_GROUP * L>(A.ctr, ec);
+
+    // ---- OU noise under the load latency: normals (2p, 2p + 1) are Box-Muller of the
+    // u32 pair (p & 1) of Philox call p / 2 of the (global env id, t, OU) stream
+    float z0 = 0.0f, z1 = 0.0f;
+    if (A.normals) {
+        if (is_ou) { z0 = A.normals[(size_t)ec * NZ + 2 * p]; z1 = A.normals[(size_t)ec * NZ + 2 * p + 1]; }
+    } else {
+        const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+        const uint4 u = philox4x32_10(make_uint4(gid, t_now, RS_STREAM_OU, (uint32_t)(p >> 1)), key);
+        const uint32_t ua = (p & 1) ? u.z : u.x, ub = (p & 1) ? u.w : u.y;
+        float sn, cs;
+        const float rr = sqrtf(-2.0f * __logf(u01(ua)));
+        __sincosf(2.0f * RS_PI_F * (u01(ub) - 0.5f), &sn, &cs);   // angle - pi: flip signs
+        z0 = -rr * cs; z1 = -rr * sn;
+    }
+
+    // ---- _get_commands, vss_gym.py:119-142 (Utils/Utils.py:14-21 OU sample)
+    if (is_ou) {
+        a.x = a.x + (float)RS_OU_THETA * (0.0f - a.x) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z0;
+        a.y = a.y + (float)RS_OU_THETA * (0.0f - a.y) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z1;
+    }
+    float wl, wr;
+    vss_action_to_wheels(P, a.x, a.y, wl, wr);
+    LaneDrive d;
+    vss_target(P, wl, wr, d.tf, d.tw);
+    d.tl = 0.0f; d.kick = 0.0f; d.drib = false;
+    if (A.cmds_out && valid && is_robot)
+        reinterpret_cast<float2 *>(A.cmds_out)[(size_t)e * R + (b - 1)] = make_float2(wl, wr);
+
+    // ---- rsim.send_commands + get_frame, vss_gym_base.py:77-82
+    lanes_physics_step<RS_KIND_VSS, L>(P, R, b, s, d);
+
+    // ---- _calculate_reward_and_done, vss_gym.py:144-192: every lane evaluates it on the
+    // ball (lane 0) and blue 0 (lane 1) and keeps the update of its own task word
+    const float bx = g.get(s.x, 0), by = g.get(s.y, 0);
+    const float r0x = g.get(s.x, 1), r0y = g.get(s.y, 1), r0vx = g.get(s.vx, 1), r0vy = g.get(s.vy, 1);
+    const float wl0 = g.get(wl, 1), wr0 = g.get(wr, 1);
+    const float prev = g.get(__uint_as_float(aux), RS_AUX_PREV);
+    const uint32_t stw = __float_as_uint(g.get(__uint_as_float(aux), RS_AUX_STEPS));
+    int steps = (int)(stw & 0xFFFFFFu);
+    bool has_prev = (stw >> 24) & 1u;
+    const bool fresh = steps == 0;
+    steps += 1;                                                 // vss_gym_base.py:73
+    float rew, prev_n = prev;
+    float dI[RS_VSS_INFO] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    bool goal = false;
+    if (bx > P.half_len) { dI[0] = 1.0f; dI[4] = 1.0f; rew = 10.0f; goal = true; }
+    else if (bx < -P.half_len) { dI[0] = -1.0f; dI[5] = 1.0f; rew = -10.0f; goal = true; }
+    else {
+        const float length_cm = 2.0f * P.half_len * 100.0f, hl = P.half_len + P.goal_depth;
+        const float dx_d = (hl + bx) * 100.0f, dx_a = (hl - bx) * 100.0f, dy = by * 100.0f;
+        const float pot = ((-sqrtf(dx_a * dx_a + 2.0f * dy * dy) + sqrtf(dx_d * dx_d + 2.0f * dy * dy)) / length_cm - 1.0f) * 0.5f;
+        float grad = 0.0f;
+        if (has_prev) grad = clampf((pot - prev) * 3.0f / P.dt, -5.0f, 5.0f);
+        prev_n = pot; has_prev = true;
+        const float rx = bx - r0x, ry = by - r0y;
+        const float rinv = rsqrtf(rx * rx + ry * ry);
+        const float move = clampf((rx * rinv * r0vx + ry * rinv * r0vy) * (1.0f / 0.4f), -5.0f, 5.0f);
+        const float energy = -(fabsf(wl0) + fabsf(wr0));
+        rew = 0.2f * move + 0.8f * grad + 2e-4f * energy;
+        dI[1] = 0.2f * move; dI[2] = 0.8f * grad; dI[3] = 2e-4f * energy;
+    }
+    const bool tr = steps >= A.max_steps;                       // TimeLimit, __init__.py:4
+    const bool reset = A.auto_reset && (goal || tr);
+    if (valid && b == 0) { A.reward[e] = rew; A.done[e] = goal ? 1 : 0; A.trunc[e] = tr ? 1 : 0; }
+    {
+        float delta = 0.0f;
+#pragma unroll
+        for (int i = 0; i < RS_VSS_INFO; ++i) if (b == RS_AUX_INFO + i) delta = dI[i];
+        uint32_t out = __float_as_uint((fresh ? 0.0f : __uint_as_float(aux)) + delta);
+        if (b == RS_AUX_PREV) out = __float_as_uint(reset ? 0.0f : prev_n);
+        if (b == RS_AUX_STEPS) out = reset ? 0u : ((uint32_t)steps | ((has_prev ? 1u : 0u) << 24));
+        if (valid) S.aux[(size_t)b * S.np + e] = out;
+    }
+    if (reset) {        // rare, uniform within the group: every lane draws the placement, keeps its body
+        Scene<0> tmp;
+        vss_place<0>(P, Rng(A.seed, gid, t_now, RS_STREAM_AUTORESET), tmp);
+        if (b == 0) { s.x = tmp.bx; s.y = tmp.by; }
+        else if (is_robot) { s.x = tmp.x[b - 1]; s.y = tmp.y[b - 1]; s.th = tmp.th[b - 1]; }
+        s.vx = 0.0f; s.vy = 0.0f; s.om = 0.0f;
+        a = make_float2(0.0f, 0.0f);
+    }
+    __syncwarp();
+    // ---- stores
+    if (valid) {
+        lanes_store<L>(S, R, b, e, s);
+        if (is_ou) S.ou[(size_t)p * S.np + e] = a;
+    }
+    // ---- observation row (vss_gym.py:93-117): ball [0, 4), blue 7 each, yellow 5 each
+    {
+        float *o = tile + el * NOBS;
+        const float nx = nrm(s.x, P.inv_max_pos), ny = nrm(s.y, P.inv_max_pos);
+        const float nvx = nrm(s.vx, P.inv_max_v), nvy = nrm(s.vy, P.inv_max_v), nw = nrm(s.om, P.inv_max_w_rad);
+        if (b == 0) { o[0] = nx; o[1] = ny; o[2] = nvx; o[3] = nvy; }
+        else if (b <= NB) {
+            float sn, cs;
+            __sincosf(s.th, &sn, &cs);
+            float *q = o + 4 + 7 * (b - 1);
+            q[0] = nx; q[1] = ny; q[2] = sn; q[3] = cs; q[4] = nvx; q[5] = nvy; q[6] = nw;
+        } else if (b <= R) {
+            float *q = o + 4 + 7 * NB + 5 * (b - NB - 1);
+            q[0] = nx; q[1] = ny; q[2] = nvx; q[3] = nvy; q[4] = nw;
+        }
+    }
+    if (valid) step_counter_bump<RS_CTR_GROUP * L>(A.ctr, e, t_now);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS);
 }
 
 struct SslStepArgs {
@@ -175,13 +321,12 @@ __global__ void __launch_bounds__(BS)
 k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
     constexpr int R = NB + NY, NOBS = 4 + 8 * NB + 2 * NY;
     __shared__ __align__(128) float tile[BS * NOBS];
-    __shared__ uint32_t s_t;
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * BS;
     const int e = e0 + tid;
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
-    const uint32_t t_now = read_and_bump_step_counter(A.ctr, &s_t);
+    const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
     if (e < S.n) {
         Scene<R> s;
         load_scene<R>(P, S, e, s);
@@ -190,6 +335,7 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
 #pragma unroll
         for (int i = 0; i < RS_SSL_INFO; ++i) info[i] = steps == 0 ? 0.0f : S.info[(size_t)i * S.np + e];
         steps += 1;
+        const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
         // ---- _get_commands + convert_actions, static_defenders.py:114-148
         float a[RS_SSL_ACT];
 #pragma unroll
@@ -218,7 +364,7 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         }
         const float lbx = s.bx, lby = s.by, lrx = s.x[0], lry = s.y[0];   // last_frame
 
-        physics_step<RS_KIND_SSL, R>(P, s, d);
+        physics_step<RS_KIND_SSL, R>(P, s, d, live);
 
         // ---- _calculate_reward_and_done, static_defenders.py:150-212 / contested_possession.py:136-208
         float rew = 0.0f; bool dn = false;
@@ -272,8 +418,188 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         store_scene<R>(P, S, e, s);
         S.steps[e] = steps;
         ssl_obs<NB, NY>(P, s, tile + tid * NOBS);
+        step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
     }
     warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS);
+}
+
+// SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step, one lane per BODY
+// (rs_lanes.cuh): L lanes per match (8 for 1 v 6, 4 for 1 v 1).  Lane b owns task words
+// b, b + L, ... of the 2 + RS_SSL_INFO words of its match.
+template <int TASK, int NB, int NY, int L, int BS>
+__global__ void __launch_bounds__(BS)
+k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
+    constexpr int R = NB + NY, NOBS = 4 + 8 * NB + 2 * NY, EPB = BS / L, MPW = 32 / L;
+    constexpr int NW = RS_AUX_INFO + RS_SSL_INFO, KW = (NW + L - 1) / L;
+    static_assert(NB == 1 && R + 1 <= L, "the benchmarked SSL tasks have one agent, blue 0");
+    __shared__ __align__(128) float tile[EPB * NOBS];
+    const int tid = threadIdx.x;
+    const int b = tid & (L - 1);
+    const int el = tid / L;
+    const int e = blockIdx.x * EPB + el;
+    const bool valid = e < S.n;
+    const int ec = valid ? e : S.n - 1;
+    const int w0 = blockIdx.x * EPB + (tid >> 5) * MPW;
+    const int wrows = min(MPW, S.n - w0);
+    const LaneGroup<L> g;
+    const bool is_robot = b >= 1 && b <= R;
+
+    LaneBody s;
+    lanes_load<L>(S, R, b, ec, s);
+    uint32_t aux[KW];
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {
+        const int w = b + k * L;                               // (word 0, the VSS ball potential, is unused here)
+        aux[k] = (w < NW && w != RS_AUX_PREV) ? S.aux[(size_t)w * S.np + ec] : 0u;
+    }
+    float a[RS_SSL_ACT];
+#pragma unroll
+    for (int i = 0; i < RS_SSL_ACT; ++i) a[i] = b == 1 ? A.actions[(size_t)ec * RS_SSL_ACT + i] : 0.0f;
+    const uint32_t t_now = step_counter_read<RS_CTR_GROUP * L>(A.ctr, ec);
+
+    // ---- _get_commands + convert_actions, static_defenders.py:114-148 (blue 0; the other
+    // robots get all-zero rows, rsim.py:129-130)
+    const float max_v = 2.5f, max_w = 10.0f, kick_speed = 5.0f;
+    float cmd[8];
+    {
+        float sn, cs;
+        __sincosf(s.th, &sn, &cs);
+        const float vx = a[0] * max_v, vy = a[1] * max_v;
+        const float lx = vx * cs + vy * sn, ly = -vx * sn + vy * cs;
+        const float vn2 = lx * lx + ly * ly;
+        const float c = vn2 < max_v * max_v ? 1.0f : max_v * rsqrtf(vn2);
+        cmd[0] = 0.0f; cmd[1] = lx * c; cmd[2] = ly * c; cmd[3] = a[2] * max_w; cmd[4] = 0.0f;
+        cmd[5] = a[3] > 0.0f ? kick_speed : 0.0f; cmd[6] = 0.0f; cmd[7] = a[4] > 0.0f ? 1.0f : 0.0f;
+    }
+    LaneDrive d;
+    ssl_target(P, cmd, d.tf, d.tl, d.tw, d.kick, d.drib);
+    if (b != 1) { d.tf = 0.0f; d.tl = 0.0f; d.tw = 0.0f; d.kick = 0.0f; d.drib = false; }
+    if (A.cmds_out && valid && is_robot) {
+        float *o = A.cmds_out + ((size_t)e * R + (b - 1)) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = b == 1 ? cmd[i] : 0.0f;
+    }
+    const float ox = s.x, oy = s.y;                              // last_frame (own body)
+
+    lanes_physics_step<RS_KIND_SSL, L>(P, R, b, s, d);
+
+    // ---- _calculate_reward_and_done, static_defenders.py:150-212 / contested_possession.py:136-208
+    const float bx = g.get(s.x, 0), by = g.get(s.y, 0), lbx = g.get(ox, 0), lby = g.get(oy, 0);
+    const float rx = g.get(s.x, 1), ry = g.get(s.y, 1), lrx = g.get(ox, 1), lry = g.get(oy, 1);
+    const float rvx = g.get(s.vx, 1), rvy = g.get(s.vy, 1), rth = g.get(s.th, 1), rom = g.get(s.om, 1);
+    int steps = (int)(__float_as_uint(g.get(__uint_as_float(aux[0]), RS_AUX_STEPS)) & 0xFFFFFFu);
+    const bool fresh = steps == 0;
+    steps += 1;
+    float rew = 0.0f; bool dn = false;
+    float dI[RS_SSL_INFO];
+#pragma unroll
+    for (int i = 0; i < RS_SSL_INFO; ++i) dI[i] = 0.0f;
+    if (TASK == RS_TASK_SSL_CONTESTED_POSSESSION) {
+        const bool moved = b > NB && b <= R && (fabsf(s.vx) > 0.1f || fabsf(s.vy) > 0.1f);
+        const int cnt = __popc(g.bits(__ballot_sync(RS_FULL_MASK, moved)));
+        if (cnt) { dI[8] = (float)cnt; dn = true; }
+    }
+    const float hl = P.half_len, hw = P.half_wid;
+    if (rx < -0.2f || fabsf(ry) > hw) { dn = true; dI[4] = 1.0f; }
+    else if (rx > hl - P.pen_len && fabsf(ry) < P.half_pen_wid) { dn = true; dI[1] = 1.0f; }
+    else if (bx < 0.0f || fabsf(by) > hw) { dn = true; dI[2] = 1.0f; }
+    else if (bx > hl) {
+        dn = true;
+        if (fabsf(by) < P.half_goal_wid) { rew = 5.0f; dI[0] = 1.0f; } else { dI[3] = 1.0f; }
+    } else {
+        const float ball_dist_scale = sqrtf(4.0f * hw * hw + hl * hl);
+        const float ball_grad_scale = sqrtf(hw * hw + hl * hl) * 0.25f;
+        const float energy_scale = 160.0f * 4.0f * (TASK == RS_TASK_SSL_STATIC_DEFENDERS ? 1000.0f : 1200.0f);
+        const float ld = sqrtf((lrx - lbx) * (lrx - lbx) + (lry - lby) * (lry - lby));
+        const float nd = sqrtf((rx - bx) * (rx - bx) + (ry - by) * (ry - by));
+        const float bd = clampf(ld - nd, -1.0f, 1.0f) / ball_dist_scale;
+        const float lg = sqrtf((hl - lbx) * (hl - lbx) + lby * lby);
+        const float ng = sqrtf((hl - bx) * (hl - bx) + by * by);
+        const float bg = clampf(lg - ng, -1.0f, 1.0f) / ball_grad_scale;
+        float sn, cs;
+        __sincosf(rth, &sn, &cs);
+        const float vf = cs * rvx + sn * rvy, vl = -sn * rvx + cs * rvy;
+        float en = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) en += fabsf((P.J[i][0] * vf + P.J[i][1] * vl + P.J[i][2] * rom) * P.inv_rw);
+        const float er = -en / energy_scale;
+        dI[5] = bd; dI[6] = bg; dI[7] = er;
+        rew = bd + bg + er;
+    }
+    const bool tr = steps >= A.max_steps;
+    const bool reset = A.auto_reset && (dn || tr);
+    if (valid && b == 0) { A.reward[e] = rew; A.done[e] = dn ? 1 : 0; A.trunc[e] = tr ? 1 : 0; }
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {
+        const int w = b + k * L;
+        float delta = 0.0f;
+#pragma unroll
+        for (int i = 0; i < RS_SSL_INFO; ++i) if (w == RS_AUX_INFO + i) delta = dI[i];
+        uint32_t out = __float_as_uint((fresh ? 0.0f : __uint_as_float(aux[k])) + delta);
+        if (w == RS_AUX_STEPS) out = reset ? 0u : (uint32_t)steps;
+        if (valid && w < NW && w != RS_AUX_PREV) S.aux[(size_t)w * S.np + e] = out;
+    }
+    if (reset) {
+        Scene<0> tmp;
+        task_place<TASK, 0>(P, Rng(A.seed, A.env_offset + (uint32_t)ec, t_now, RS_STREAM_AUTORESET), tmp);
+        if (b == 0) { s.x = tmp.bx; s.y = tmp.by; }
+        else if (is_robot) { s.x = tmp.x[b - 1]; s.y = tmp.y[b - 1]; s.th = tmp.th[b - 1]; }
+        s.vx = 0.0f; s.vy = 0.0f; s.om = 0.0f;
+    }
+    __syncwarp();
+    if (valid) lanes_store<L>(S, R, b, e, s);
+    // ---- observation row (static_defenders.py:90-112): ball 4, blue 8 (with infrared), yellow x y
+    {
+        const float nbx = g.get(s.x, 0), nby = g.get(s.y, 0);       // ball after a possible reset
+        const float inv_v = 1.0f / 2.5f, inv_w = RS_DEG_F / 10.0f;  // quirks preserved, SURVEY A.1
+        float *o = tile + el * NOBS;
+        const float nx = nrm(s.x, P.inv_max_pos), ny = nrm(s.y, P.inv_max_pos);
+        if (b == 0) { o[0] = nx; o[1] = ny; o[2] = nrm(s.vx, inv_v); o[3] = nrm(s.vy, inv_v); }
+        else if (b <= NB) {
+            float sn, cs;
+            __sincosf(s.th, &sn, &cs);
+            float *q = o + 4 + 8 * (b - 1);
+            q[0] = nx; q[1] = ny; q[2] = sn; q[3] = cs;
+            q[4] = nrm(s.vx, inv_v); q[5] = nrm(s.vy, inv_v); q[6] = nrm(s.om, inv_w);
+            q[7] = touching(P, s.x, s.y, cs, sn, nbx, nby) ? 1.0f : 0.0f;
+        } else if (b <= R) {
+            float *q = o + 4 + 8 * NB + 2 * (b - NB - 1);
+            q[0] = nx; q[1] = ny;
+        }
+    }
+    if (valid) step_counter_bump<RS_CTR_GROUP * L>(A.ctr, e, t_now);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS);
+}
+
+// simulator.step(cmds), one lane per BODY: any (kind, R <= 31) with L = 2^k >= R + 1
+template <int KIND, int L, int BS>
+__global__ void __launch_bounds__(BS)
+k_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, const float *__restrict__ cmds) {
+    const int R = P.n_robots;
+    const int tid = threadIdx.x;
+    const int b = tid & (L - 1);
+    const int e = blockIdx.x * (BS / L) + tid / L;
+    const bool valid = e < S.n;
+    const int ec = valid ? e : S.n - 1;
+    const bool is_robot = b >= 1 && b <= R;
+    LaneBody s;
+    lanes_load<L>(S, R, b, ec, s);
+    LaneDrive d;
+    d.tf = 0.0f; d.tl = 0.0f; d.tw = 0.0f; d.kick = 0.0f; d.drib = false;
+    if (is_robot) {
+        if (KIND == RS_KIND_VSS) {
+            const float2 c = reinterpret_cast<const float2 *>(cmds)[(size_t)ec * R + (b - 1)];
+            vss_target(P, c.x, c.y, d.tf, d.tw);
+        } else {
+            const float4 *c4 = reinterpret_cast<const float4 *>(cmds) + ((size_t)ec * R + (b - 1)) * 2;
+            const float4 lo = c4[0], hi = c4[1];
+            const float cmd[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            ssl_target(P, cmd, d.tf, d.tl, d.tw, d.kick, d.drib);
+        }
+    }
+    __syncwarp();
+    lanes_physics_step<KIND, L>(P, R, b, s, d);
+    if (valid) lanes_store<L>(S, R, b, e, s);
 }
 
 // simulator.step(cmds): physics only, any (kind, R).  RT > 0: register resident scene.
@@ -281,6 +607,7 @@ template <int KIND, int RT, int BS>
 __global__ void __launch_bounds__(BS)
 k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__restrict__ cmds) {
     const int e = blockIdx.x * BS + threadIdx.x;
+    const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
     if (e >= S.n) return;
     const int R = RT > 0 ? RT : P.n_robots;
     Scene<RT> s;
@@ -306,7 +633,7 @@ k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__re
             if (drib) d.drib |= 1u << r;
         }
     }
-    physics_step<KIND, RT>(P, s, d);
+    physics_step<KIND, RT>(P, s, d, live);
     store_scene<RT>(P, S, e, s);
 }
 
@@ -401,10 +728,10 @@ template <int TASK>
 __global__ void k_task_reset(const DevParams P, const StatePtrs S, const uint8_t *__restrict__ mask,
                              float *__restrict__ obs, int obs_dim, uint64_t seed,
                              const uint32_t *__restrict__ ctr, uint32_t env_offset) {
-    const uint32_t t = *ctr;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= S.n) return;
     if (mask && !mask[e]) return;
+    const uint32_t t = ctr[e / RS_CTR_GROUP];
     Scene<0> s;
     task_place<TASK, 0>(P, Rng(seed, env_offset + (uint32_t)e, t, RS_STREAM_RESET), s);
     store_scene<0>(P, S, e, s);
@@ -457,12 +784,15 @@ struct rs_world {
     int64_t env_offset;
     uint64_t t;              // host mirror of d_ctr[0]
     bool t_dirty;            // host t changed without the device counter (rs_step, rs_set_t)
-    uint32_t *d_ctr;         // device: [0] t, [1] CTAs done (library-owned scratch)
+    uint32_t *d_ctr;         // device: t, one copy per RS_CTR_GROUP matches (library-owned)
+    int n_ctr;
     uint64_t launches;
     void *state;
     int64_t off[RS_ARR_COUNT];
     size_t state_bytes;
     int block;               // CTA size of the step kernels
+    int per_match;           // 1: one lane per MATCH kernels (rs_device.cuh); 0: one lane per BODY (rs_lanes.cuh)
+    int lane_block;          // CTA size of the lane-per-body kernels
     // scratch for the *_host entry points (library owned)
     float *s_actions, *s_obs, *s_reward;
     uint8_t *s_done, *s_trunc;
@@ -517,6 +847,7 @@ static StatePtrs state_ptrs(const rs_world *w) {
     S.prev = (float *)(b + w->off[RS_ARR_PREV]);
     S.steps = (int *)(b + w->off[RS_ARR_STEPS]);
     S.info = (float *)(b + w->off[RS_ARR_INFO]);
+    S.aux = (uint32_t *)(b + w->off[RS_ARR_PREV]);     // PREV, STEPS, INFO are back to back (rs_create)
     S.n = w->n; S.np = w->np;
     return S;
 }
@@ -526,6 +857,24 @@ static void launch_step(rs_world *w, const float *cmds, cudaStream_t st) {
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
     if (w->block == 128) k_step<KIND, RT, 128><<<g128, 128, 0, st>>>(w->dp, state_ptrs(w), cmds);
     else k_step<KIND, RT, 64><<<g64, 64, 0, st>>>(w->dp, state_ptrs(w), cmds);
+}
+
+// lane-per-body launches: grid = matches / (BS / L)
+template <int KIND, int L>
+static void launch_step_lanes_l(rs_world *w, const float *cmds, cudaStream_t st) {
+    const StatePtrs S = state_ptrs(w);
+    if (w->lane_block == 256) k_step_lanes<KIND, L, 256><<<(w->n + 256 / L - 1) / (256 / L), 256, 0, st>>>(w->dp, S, cmds);
+    else if (w->lane_block == 64) k_step_lanes<KIND, L, 64><<<(w->n + 64 / L - 1) / (64 / L), 64, 0, st>>>(w->dp, S, cmds);
+    else k_step_lanes<KIND, L, 128><<<(w->n + 128 / L - 1) / (128 / L), 128, 0, st>>>(w->dp, S, cmds);
+}
+template <int KIND>
+static void launch_step_lanes(rs_world *w, const float *cmds, cudaStream_t st) {
+    const int bodies = w->p.n_robots + 1;
+    if (bodies <= 2) launch_step_lanes_l<KIND, 2>(w, cmds, st);
+    else if (bodies <= 4) launch_step_lanes_l<KIND, 4>(w, cmds, st);
+    else if (bodies <= 8) launch_step_lanes_l<KIND, 8>(w, cmds, st);
+    else if (bodies <= 16) launch_step_lanes_l<KIND, 16>(w, cmds, st);
+    else launch_step_lanes_l<KIND, 32>(w, cmds, st);
 }
 
 extern "C" {
@@ -566,8 +915,12 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     w->off[RS_ARR_INFO] = (int64_t)o; o += 4 * (size_t)RS_SSL_INFO * np;
     w->state_bytes = o;
     w->block = 64;
+    w->per_match = 0; w->lane_block = 128;
+    if (const char *ls = getenv("RS_PER_MATCH")) w->per_match = atoi(ls) != 0;
+    if (const char *bs = getenv("RS_LANE_BLOCK")) { const int b = atoi(bs); if (b == 64 || b == 128 || b == 256) w->lane_block = b; }
     if (const char *bs = getenv("RS_BLOCK")) { const int b = atoi(bs); if (b == 32 || b == 64 || b == 128 || b == 256) w->block = b; }
-    if (cudaMalloc(&w->d_ctr, 2 * sizeof(uint32_t)) != cudaSuccess || cudaMemset(w->d_ctr, 0, 2 * sizeof(uint32_t)) != cudaSuccess) {
+    w->n_ctr = w->np / RS_CTR_GROUP;
+    if (cudaMalloc(&w->d_ctr, w->n_ctr * sizeof(uint32_t)) != cudaSuccess || cudaMemset(w->d_ctr, 0, w->n_ctr * sizeof(uint32_t)) != cudaSuccess) {
         delete w;
         return fail(RS_E_CUDA, "rs_create: cudaMalloc of the step counter failed");
     }
@@ -630,7 +983,10 @@ int rs_step(rs_world *w, const float *d_cmds, void *stream) {
     if (!d_cmds) return fail(RS_E_INVALID, "rs_step: null commands");
     cudaStream_t st = (cudaStream_t)stream;
     const int R = w->p.n_robots;
-    if (w->p.kind == RS_KIND_VSS) {
+    if (!w->per_match) {
+        if (w->p.kind == RS_KIND_VSS) launch_step_lanes<RS_KIND_VSS>(w, d_cmds, st);
+        else launch_step_lanes<RS_KIND_SSL>(w, d_cmds, st);
+    } else if (w->p.kind == RS_KIND_VSS) {
         if (R == 6) launch_step<RS_KIND_VSS, 6>(w, d_cmds, st);
         else if (R == 10) launch_step<RS_KIND_VSS, 10>(w, d_cmds, st);
         else if (R == 2) launch_step<RS_KIND_VSS, 2>(w, d_cmds, st);
@@ -691,7 +1047,7 @@ uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches : 0; }
 
 static void push_t(rs_world *w, cudaStream_t st) {
     if (!w->t_dirty) return;
-    k_set_ctr<<<1, 1, 0, st>>>(w->d_ctr, (uint32_t)w->t);
+    k_set_ctr<<<(w->n_ctr + 255) / 256, 256, 0, st>>>(w->d_ctr, w->n_ctr, (uint32_t)w->t);
     w->launches++; w->t_dirty = false;
 }
 
@@ -744,7 +1100,11 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
     push_t(w, st);
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
-    switch (w->block) {
+    if (!w->per_match) {
+        if (w->lane_block == 256) k_vss_env_step_lanes<256><<<(w->n + 31) / 32, 256, 0, st>>>(w->dp, S, A);
+        else if (w->lane_block == 64) k_vss_env_step_lanes<64><<<(w->n + 7) / 8, 64, 0, st>>>(w->dp, S, A);
+        else k_vss_env_step_lanes<128><<<(w->n + 15) / 16, 128, 0, st>>>(w->dp, S, A);
+    } else switch (w->block) {
         case 32: k_vss_env_step<3, 3, 32><<<(w->n + 31) / 32, 32, 0, st>>>(w->dp, S, A); break;
         case 128: k_vss_env_step<3, 3, 128><<<(w->n + 127) / 128, 128, 0, st>>>(w->dp, S, A); break;
         case 256: k_vss_env_step<3, 3, 256><<<(w->n + 255) / 256, 256, 0, st>>>(w->dp, S, A); break;
@@ -772,7 +1132,19 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
-    if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
+    if (!w->per_match) {
+        // lane per body: 8 lanes per 1 v 6 match, 4 per 1 v 1 match
+        const int bs = w->lane_block;
+        if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
+            if (bs == 256) k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 256><<<(w->n + 31) / 32, 256, 0, st>>>(w->dp, S, A);
+            else if (bs == 64) k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 64><<<(w->n + 7) / 8, 64, 0, st>>>(w->dp, S, A);
+            else k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 128><<<(w->n + 15) / 16, 128, 0, st>>>(w->dp, S, A);
+        } else {
+            if (bs == 256) k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 256><<<(w->n + 63) / 64, 256, 0, st>>>(w->dp, S, A);
+            else if (bs == 64) k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 64><<<(w->n + 15) / 16, 64, 0, st>>>(w->dp, S, A);
+            else k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 128><<<(w->n + 31) / 32, 128, 0, st>>>(w->dp, S, A);
+        }
+    } else if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
         if (w->block == 128) k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 128><<<g128, 128, 0, st>>>(w->dp, S, A);
         else k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 64><<<g64, 64, 0, st>>>(w->dp, S, A);
     } else {

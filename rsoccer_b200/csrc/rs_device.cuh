@@ -261,6 +261,38 @@ __device__ __forceinline__ void robot_robot(const DevParams &P, float xi, float 
     any = true;
 }
 
+// pair k of the lexicographic order [ball x robots 0..R-1, then robot pairs i < j] -> (i, j)
+template <int R> __host__ __device__ constexpr int rr_pair_i(int k) {
+    int i = 0;
+    while (k >= R - 1 - i) { k -= R - 1 - i; ++i; }
+    return i;
+}
+template <int R> __host__ __device__ constexpr int rr_pair_j(int k) {
+    int i = 0;
+    while (k >= R - 1 - i) { k -= R - 1 - i; ++i; }
+    return i + 1 + k;
+}
+// warp-uniform jump to the register-static body of pair p in [LO, HI): a binary decision tree
+template <int KIND, int RT, int LO, int HI>
+struct PairDispatch {
+    static __device__ __forceinline__ void run(const int p, const DevParams &P, Scene<RT> &s, float &cbx, float &cby,
+                                               float (&cx)[Cap<RT>::v], float (&cy)[Cap<RT>::v], bool &any) {
+        if constexpr (HI - LO == 1) {
+            if constexpr (LO < RT) {
+                ball_robot<KIND>(P, s.bx, s.by, s.bvx, s.bvy, s.x[LO], s.y[LO], s.th[LO], s.vx[LO], s.vy[LO], s.om[LO],
+                                 cbx, cby, cx[LO], cy[LO], any);
+            } else {
+                constexpr int i = rr_pair_i<RT>(LO - RT), j = rr_pair_j<RT>(LO - RT);
+                robot_robot(P, s.x[i], s.y[i], s.vx[i], s.vy[i], s.x[j], s.y[j], s.vx[j], s.vy[j], cx[i], cy[i], cx[j], cy[j], any);
+            }
+        } else {
+            constexpr int MID = (LO + HI) / 2;
+            if (p < MID) PairDispatch<KIND, RT, LO, MID>::run(p, P, s, cbx, cby, cx, cy, any);
+            else PairDispatch<KIND, RT, MID, HI>::run(p, P, s, cbx, cby, cx, cy, any);
+        }
+    }
+};
+
 // commands -> drive targets.  VSS: cmd = (wl, wr) rad/s (rsim.py:100-101)
 __device__ __forceinline__ void vss_target(const DevParams &P, float wl, float wr, float &tf, float &tw) {
     wl = clampf(wl, -P.wmax, P.wmax); wr = clampf(wr, -P.wmax, P.wmax);
@@ -287,7 +319,8 @@ __device__ __forceinline__ void ssl_target(const DevParams &P, const float (&cmd
 
 // ---------------------------------------------------------------- one control step
 template <int KIND, int RT>
-__device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, const Drive<RT> &d) {
+__device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, const Drive<RT> &d,
+                                             const unsigned live /* lanes of this warp that call */) {
     const int R = RT > 0 ? RT : P.n_robots;
     const float h = P.h;
     uint32_t kicked = 0;
@@ -363,9 +396,50 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
         // velocity impulses applied sequentially, position corrections summed and applied
         // afterwards.  A contact is rare per lane (~7 % of the matches have one at any time,
         // tools/contact_stats.py) but in a warp of 32 matches "some lane has one" holds for
-        // ~90 % of the sub-steps, spread over the 21 pairs: the resolution bodies stay inline
-        // per pair (a spilled generic resolver was measured 40 % slower) and are hinted cold.
-        {
+        // ~90 % of the sub-steps, spread over the pairs.  Up to 28 pairs (R <= 7):
+        //   1. detection is straight-line -- one mask bit per pair, no branch, full ILP;
+        //   2. the masks are OR-reduced over the warp (REDUX) and the warp walks the set bits
+        //      in ascending (= lexicographic) order, jumping to the register-static body of
+        //      that pair; lanes without that contact fail the body's own distance test.
+        // The hot path is thus branch-free and contiguous (no taken branch over a cold body
+        // per pair: the kernel was instruction-fetch bound, profiles/r1_steady_final.txt).
+        if (RT > 0 && RT <= 7) {
+            uint32_t mask = 0;
+            {
+                int bit = 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float dx = s.bx - s.x[r], dy = s.by - s.y[r];
+                    if (dx * dx + dy * dy < P.rs_br2) mask |= 1u << bit;
+                    ++bit;
+                }
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+#pragma unroll
+                    for (int j = i + 1; j < R; ++j) {
+                        const float dx = s.x[j] - s.x[i], dy = s.y[j] - s.y[i];
+                        if (dx * dx + dy * dy < P.rs_rr2) mask |= 1u << bit;
+                        ++bit;
+                    }
+                }
+            }
+            uint32_t wm = __reduce_or_sync(live, mask);
+            if (wm) {
+                float cbx = 0.0f, cby = 0.0f;
+                float cx[Cap<RT>::v], cy[Cap<RT>::v];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { cx[r] = 0.0f; cy[r] = 0.0f; }
+                bool any = false;
+                do {
+                    const int p = __ffs((int)wm) - 1;
+                    wm &= wm - 1;
+                    PairDispatch<KIND, RT, 0, RT + RT * (RT - 1) / 2>::run(p, P, s, cbx, cby, cx, cy, any);
+                } while (wm);
+                s.bx += cbx; s.by += cby;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { s.x[r] += cx[r]; s.y[r] += cy[r]; }
+            }
+        } else {
             float cbx = 0.0f, cby = 0.0f;
             float cx[Cap<RT>::v], cy[Cap<RT>::v];
 #pragma unroll
@@ -403,6 +477,7 @@ struct StatePtrs {
     float *prev;      // [Np]
     int *steps;       // [Np]
     float *info;      // [RS_SSL_INFO][Np]
+    uint32_t *aux;    // [2 + RS_SSL_INFO][Np] = prev, steps, info seen as one array of task words (rs_lanes.cuh)
     int n;            // envs
     int np;           // padded env count (array pitch)
 };
@@ -457,18 +532,23 @@ __device__ __forceinline__ void warp_tile_store(float *gdst, const float *stile,
     }
 }
 
-// World step counter (Philox counter word 1) in device memory, so that a captured CUDA
-// graph replays with fresh counters.  Thread 0 reads ctr[0], publishes it through smem,
-// and only then registers the CTA at ctr[1]; the CTA that registers last bumps ctr[0]
-// (every CTA has read it by then; the next launch is stream ordered).  Done on ENTRY so
-// that the atomic's latency hides under the state loads instead of the kernel tail.
-__device__ __forceinline__ uint32_t read_and_bump_step_counter(uint32_t *ctr, uint32_t *s_t) {
-    if (threadIdx.x == 0) {
-        const uint32_t t = *reinterpret_cast<volatile uint32_t *>(ctr);
-        *s_t = t;
-        const uint32_t prev = atomicAdd(&ctr[1], 1u);
-        if (prev == gridDim.x - 1) { ctr[1] = 0u; ctr[0] = t + 1u; }
-    }
-    __syncthreads();
-    return *s_t;
+// World step counter t (Philox counter word 1) in device memory, so that a captured CUDA
+// graph replays with fresh counters.  One copy per group of RS_CTR_GROUP consecutive matches,
+// all copies equal (every step kernel advances every match): the first lane of a group
+// reads its copy, the group gets it by shuffle, and the same lane stores t + 1 at the end
+// of the kernel.  No atomics, no CTA barrier, no hot address (a single shared counter with a
+// "last CTA bumps it" ticket cost 8 % of the stall samples, profiles/r1_steady_final.txt),
+// and no race: reader and writer of a copy are the same thread.
+//   GL = lanes per counter group = RS_CTR_GROUP x lanes per match (a divisor of 32).
+#define RS_CTR_GROUP 4
+template <int GL>
+__device__ __forceinline__ uint32_t step_counter_read(const uint32_t *ctr, const int e, const unsigned live = 0xffffffffu) {
+    const int lane = threadIdx.x & 31;
+    uint32_t t = 0u;
+    if ((lane & (GL - 1)) == 0) t = ctr[e / RS_CTR_GROUP];
+    return __shfl_sync(live, t, lane & ~(GL - 1));      // a group's first lane is live whenever any of its lanes is
+}
+template <int GL>
+__device__ __forceinline__ void step_counter_bump(uint32_t *ctr, const int e, const uint32_t t) {
+    if (((threadIdx.x & 31) & (GL - 1)) == 0) ctr[e / RS_CTR_GROUP] = t + 1u;
 }
