@@ -304,12 +304,14 @@ def main():
                        "field_type": 0, "time_step_ms": 25, "substeps": 5,
                        "l2": "inputs larger than L2: %d independent %d-env worlds rotated (%.0f MB per pass > 126 MB L2)"
                              % (M, N, M * N * ALG_BYTES_PER_ENV_STEP / 1e6),
-                       "launch": "cuda graph replay" if graph is not None else "direct launches",
+                       "launch": ("cuda graph replay" if graph is not None else "direct launches")
+                                 + ", programmatic dependent launch between consecutive steps",
                        "parallelism": "env-sharded x%d, no collective on the step path" % world},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": Ke, "ms_per_step": ms_e2e / Ke,
                     "h2d_bytes_per_step": N * 2 * 4, "d2h_bytes_per_step": N * (40 * 4 + 4 + 1 + 1),
-                    "api": "rs_vss_env_step_host (pinned host buffers, H2D + kernel + D2H + sync)"},
+                    "api": "rs_vss_env_step_host (pinned host buffers, H2D + kernel + D2H + sync)",
+                    "pcie_gbs": (N * 2 * 4 + N * (40 * 4 + 4 + 1 + 1)) / (ms_e2e * 1e-3 / Ke) / 1e9},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -46,6 +46,8 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
+    pdl_wait();
+    pdl_release();
     if (e < S.n) {
         // ---- every global load of the step is issued first ...
         Scene<R> s;
@@ -188,6 +190,8 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     const int p = is_ou ? b - 2 : 0;                           // OU process of this lane (blue 0 is the agent)
     const uint32_t gid = A.env_offset + (uint32_t)ec;
 
+    pdl_wait();
+    pdl_release();
     // ---- loads first: own body, own task word, own action source
     LaneBody s;
     lanes_load<L>(S, R, b, ec, s);
@@ -327,6 +331,8 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
+    pdl_wait();
+    pdl_release();
     if (e < S.n) {
         Scene<R> s;
         load_scene<R>(P, S, e, s);
@@ -444,6 +450,8 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     const LaneGroup<L> g;
     const bool is_robot = b >= 1 && b <= R;
 
+    pdl_wait();
+    pdl_release();
     LaneBody s;
     lanes_load<L>(S, R, b, ec, s);
     uint32_t aux[KW];
@@ -582,6 +590,8 @@ k_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, const float
     const bool valid = e < S.n;
     const int ec = valid ? e : S.n - 1;
     const bool is_robot = b >= 1 && b <= R;
+    pdl_wait();
+    pdl_release();
     LaneBody s;
     lanes_load<L>(S, R, b, ec, s);
     LaneDrive d;
@@ -608,6 +618,8 @@ __global__ void __launch_bounds__(BS)
 k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__restrict__ cmds) {
     const int e = blockIdx.x * BS + threadIdx.x;
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
+    pdl_wait();
+    pdl_release();
     if (e >= S.n) return;
     const int R = RT > 0 ? RT : P.n_robots;
     Scene<RT> s;
@@ -791,7 +803,7 @@ struct rs_world {
     int64_t off[RS_ARR_COUNT];
     size_t state_bytes;
     int block;               // CTA size of the step kernels
-    int per_match;           // 1: one lane per MATCH kernels (rs_device.cuh); 0: one lane per BODY (rs_lanes.cuh)
+    int per_match;           // 1: one lane per MATCH kernels (rs_device.cuh); 0: one lane per BODY (rs_lanes.cuh); -1: by world size
     int lane_block;          // CTA size of the lane-per-body kernels
     // scratch for the *_host entry points (library owned)
     float *s_actions, *s_obs, *s_reward;
@@ -852,20 +864,55 @@ static StatePtrs state_ptrs(const rs_world *w) {
     return S;
 }
 
+
+// Which mapping steps this world?  One lane per MATCH issues the fewest instructions but
+// needs n / 32 warps of ~120 registers to fill 592 SM sub-partitions; one lane per BODY
+// issues ~2.6x the instructions in 8x the warps.  Measured on B200 with
+// tools/step_timing.py, us per step, lane per body vs lane per match:
+//   VSS-v0 3 v 3        7.5 vs 12.0 @ 4 096    12.4 vs 12.7 @ 16 384    16.6 vs 14.5 @ 24 576    36.0 vs 21.8 @ 65 536
+//   SSL 1 v 6 task      9.8 vs 13.3 @ 4 096    14.9 vs 14.2 @ 16 384    37.6 vs 30.6 @ 65 536
+//   SSL 1 v 1 task      8.3 vs  6.5 @ 4 096    10.3 vs  7.0 @ 16 384    24.0 vs 11.9 @ 65 536
+//   rs_step SSL 1 v 6 (all seven robots driven)  8.6 vs 24.8 @ 4 096    36.1 vs 57.4 @ 65 536
+// Worlds with more than 7 robots have no register-resident lane-per-match kernel (its
+// generic variant keeps the scene in local memory), so they always go lane per body.
+static bool use_lane_per_body(const rs_world *w, bool task_kernel) {
+    if (w->per_match >= 0) return w->per_match == 0;
+    const int R = w->p.n_robots;
+    if (R > 7) return true;
+    if (R <= 2) return false;
+    if (w->p.kind == RS_KIND_VSS) return w->n < 20000;
+    return task_kernel ? w->n < 14000 : true;
+}
+
+// Launch of a step kernel, by default with programmatic stream serialization (PDL): the
+// kernel's pre-wait part overlaps the tail of its predecessor in the stream (rs_device.cuh).
+static bool g_pdl = true;
+template <typename... KArgs, typename... Args>
+static void launch_step_kernel(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int KIND, int RT>
 static void launch_step(rs_world *w, const float *cmds, cudaStream_t st) {
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
-    if (w->block == 128) k_step<KIND, RT, 128><<<g128, 128, 0, st>>>(w->dp, state_ptrs(w), cmds);
-    else k_step<KIND, RT, 64><<<g64, 64, 0, st>>>(w->dp, state_ptrs(w), cmds);
+    if (w->block == 128) launch_step_kernel(k_step<KIND, RT, 128>, g128, 128, st, w->dp, state_ptrs(w), cmds);
+    else launch_step_kernel(k_step<KIND, RT, 64>, g64, 64, st, w->dp, state_ptrs(w), cmds);
 }
 
 // lane-per-body launches: grid = matches / (BS / L)
 template <int KIND, int L>
 static void launch_step_lanes_l(rs_world *w, const float *cmds, cudaStream_t st) {
     const StatePtrs S = state_ptrs(w);
-    if (w->lane_block == 256) k_step_lanes<KIND, L, 256><<<(w->n + 256 / L - 1) / (256 / L), 256, 0, st>>>(w->dp, S, cmds);
-    else if (w->lane_block == 64) k_step_lanes<KIND, L, 64><<<(w->n + 64 / L - 1) / (64 / L), 64, 0, st>>>(w->dp, S, cmds);
-    else k_step_lanes<KIND, L, 128><<<(w->n + 128 / L - 1) / (128 / L), 128, 0, st>>>(w->dp, S, cmds);
+    if (w->lane_block == 256) launch_step_kernel(k_step_lanes<KIND, L, 256>, (w->n + 256 / L - 1) / (256 / L), 256, st, w->dp, S, cmds);
+    else if (w->lane_block == 64) launch_step_kernel(k_step_lanes<KIND, L, 64>, (w->n + 64 / L - 1) / (64 / L), 64, st, w->dp, S, cmds);
+    else launch_step_kernel(k_step_lanes<KIND, L, 128>, (w->n + 128 / L - 1) / (128 / L), 128, st, w->dp, S, cmds);
 }
 template <int KIND>
 static void launch_step_lanes(rs_world *w, const float *cmds, cudaStream_t st) {
@@ -915,8 +962,9 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     w->off[RS_ARR_INFO] = (int64_t)o; o += 4 * (size_t)RS_SSL_INFO * np;
     w->state_bytes = o;
     w->block = 64;
-    w->per_match = 0; w->lane_block = 128;
+    w->per_match = -1; w->lane_block = 128;
     if (const char *ls = getenv("RS_PER_MATCH")) w->per_match = atoi(ls) != 0;
+    if (const char *ls = getenv("RS_PDL")) g_pdl = atoi(ls) != 0;
     if (const char *bs = getenv("RS_LANE_BLOCK")) { const int b = atoi(bs); if (b == 64 || b == 128 || b == 256) w->lane_block = b; }
     if (const char *bs = getenv("RS_BLOCK")) { const int b = atoi(bs); if (b == 32 || b == 64 || b == 128 || b == 256) w->block = b; }
     w->n_ctr = w->np / RS_CTR_GROUP;
@@ -983,12 +1031,13 @@ int rs_step(rs_world *w, const float *d_cmds, void *stream) {
     if (!d_cmds) return fail(RS_E_INVALID, "rs_step: null commands");
     cudaStream_t st = (cudaStream_t)stream;
     const int R = w->p.n_robots;
-    if (!w->per_match) {
+    if (use_lane_per_body(w, false)) {
         if (w->p.kind == RS_KIND_VSS) launch_step_lanes<RS_KIND_VSS>(w, d_cmds, st);
         else launch_step_lanes<RS_KIND_SSL>(w, d_cmds, st);
     } else if (w->p.kind == RS_KIND_VSS) {
         if (R == 6) launch_step<RS_KIND_VSS, 6>(w, d_cmds, st);
         else if (R == 10) launch_step<RS_KIND_VSS, 10>(w, d_cmds, st);
+        else if (R == 3) launch_step<RS_KIND_VSS, 3>(w, d_cmds, st);
         else if (R == 2) launch_step<RS_KIND_VSS, 2>(w, d_cmds, st);
         else launch_step<RS_KIND_VSS, 0>(w, d_cmds, st);
     } else {
@@ -1100,15 +1149,15 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
     push_t(w, st);
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
-    if (!w->per_match) {
-        if (w->lane_block == 256) k_vss_env_step_lanes<256><<<(w->n + 31) / 32, 256, 0, st>>>(w->dp, S, A);
-        else if (w->lane_block == 64) k_vss_env_step_lanes<64><<<(w->n + 7) / 8, 64, 0, st>>>(w->dp, S, A);
-        else k_vss_env_step_lanes<128><<<(w->n + 15) / 16, 128, 0, st>>>(w->dp, S, A);
+    if (use_lane_per_body(w, true)) {
+        if (w->lane_block == 256) launch_step_kernel(k_vss_env_step_lanes<256>, (w->n + 31) / 32, 256, st, w->dp, S, A);
+        else if (w->lane_block == 64) launch_step_kernel(k_vss_env_step_lanes<64>, (w->n + 7) / 8, 64, st, w->dp, S, A);
+        else launch_step_kernel(k_vss_env_step_lanes<128>, (w->n + 15) / 16, 128, st, w->dp, S, A);
     } else switch (w->block) {
-        case 32: k_vss_env_step<3, 3, 32><<<(w->n + 31) / 32, 32, 0, st>>>(w->dp, S, A); break;
-        case 128: k_vss_env_step<3, 3, 128><<<(w->n + 127) / 128, 128, 0, st>>>(w->dp, S, A); break;
-        case 256: k_vss_env_step<3, 3, 256><<<(w->n + 255) / 256, 256, 0, st>>>(w->dp, S, A); break;
-        default: k_vss_env_step<3, 3, 64><<<(w->n + 63) / 64, 64, 0, st>>>(w->dp, S, A); break;
+        case 32: launch_step_kernel(k_vss_env_step<3, 3, 32>, (w->n + 31) / 32, 32, st, w->dp, S, A); break;
+        case 128: launch_step_kernel(k_vss_env_step<3, 3, 128>, (w->n + 127) / 128, 128, st, w->dp, S, A); break;
+        case 256: launch_step_kernel(k_vss_env_step<3, 3, 256>, (w->n + 255) / 256, 256, st, w->dp, S, A); break;
+        default: launch_step_kernel(k_vss_env_step<3, 3, 64>, (w->n + 63) / 64, 64, st, w->dp, S, A); break;
     }
     w->launches++; w->t++;
     CUDA_TRY(cudaGetLastError());
@@ -1132,24 +1181,24 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
-    if (!w->per_match) {
+    if (use_lane_per_body(w, true)) {
         // lane per body: 8 lanes per 1 v 6 match, 4 per 1 v 1 match
         const int bs = w->lane_block;
         if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
-            if (bs == 256) k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 256><<<(w->n + 31) / 32, 256, 0, st>>>(w->dp, S, A);
-            else if (bs == 64) k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 64><<<(w->n + 7) / 8, 64, 0, st>>>(w->dp, S, A);
-            else k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 128><<<(w->n + 15) / 16, 128, 0, st>>>(w->dp, S, A);
+            if (bs == 256) launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 256>, (w->n + 31) / 32, 256, st, w->dp, S, A);
+            else if (bs == 64) launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 64>, (w->n + 7) / 8, 64, st, w->dp, S, A);
+            else launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 128>, (w->n + 15) / 16, 128, st, w->dp, S, A);
         } else {
-            if (bs == 256) k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 256><<<(w->n + 63) / 64, 256, 0, st>>>(w->dp, S, A);
-            else if (bs == 64) k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 64><<<(w->n + 15) / 16, 64, 0, st>>>(w->dp, S, A);
-            else k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 128><<<(w->n + 31) / 32, 128, 0, st>>>(w->dp, S, A);
+            if (bs == 256) launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 256>, (w->n + 63) / 64, 256, st, w->dp, S, A);
+            else if (bs == 64) launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 64>, (w->n + 15) / 16, 64, st, w->dp, S, A);
+            else launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 128>, (w->n + 31) / 32, 128, st, w->dp, S, A);
         }
     } else if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
-        if (w->block == 128) k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 128><<<g128, 128, 0, st>>>(w->dp, S, A);
-        else k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 64><<<g64, 64, 0, st>>>(w->dp, S, A);
+        if (w->block == 128) launch_step_kernel(k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 128>, g128, 128, st, w->dp, S, A);
+        else launch_step_kernel(k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 64>, g64, 64, st, w->dp, S, A);
     } else {
-        if (w->block == 128) k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 128><<<g128, 128, 0, st>>>(w->dp, S, A);
-        else k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 64><<<g64, 64, 0, st>>>(w->dp, S, A);
+        if (w->block == 128) launch_step_kernel(k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 128>, g128, 128, st, w->dp, S, A);
+        else launch_step_kernel(k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 64>, g64, 64, st, w->dp, S, A);
     }
     w->launches++; w->t++;
     CUDA_TRY(cudaGetLastError());

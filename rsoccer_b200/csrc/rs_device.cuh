@@ -552,3 +552,12 @@ template <int GL>
 __device__ __forceinline__ void step_counter_bump(uint32_t *ctr, const int e, const uint32_t t) {
     if (((threadIdx.x & 31) & (GL - 1)) == 0) ctr[e / RS_CTR_GROUP] = t + 1u;
 }
+
+// Programmatic dependent launch (sm_90+): a step kernel launched with the
+// programmaticStreamSerialization attribute may start while its predecessor in the stream is
+// still draining.  Everything before pdl_wait() must touch only kernel parameters; after it
+// the predecessor's writes are visible.  pdl_release() lets the NEXT launch begin its own
+// pre-wait part (launch latency, parameter fetch, CTA placement hide under this kernel).
+// Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -20,10 +20,19 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
-def engine():
+def _engine_module():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from rsoccer_b200 import _lib, engine as E
     _lib.lib()          # fails loudly if the extension is not built
     return E
+
+
+@pytest.fixture(params=["per_match", "per_body"])
+def engine(request, monkeypatch, _engine_module):
+    """The CUDA engine, once per kernel mapping: rs_create reads RS_PER_MATCH (1 = one lane
+    per match, rs_device.cuh; 0 = one lane per body, rs_lanes.cuh; unset = by world size),
+    so every GPU test exercises both families whatever the size heuristic would pick."""
+    monkeypatch.setenv("RS_PER_MATCH", "1" if request.param == "per_match" else "0")
+    return _engine_module

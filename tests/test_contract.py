@@ -44,8 +44,9 @@ class Sim:
         return self.state()[:, 5 + self.K * r:5 + self.K * (r + 1)]
 
 
-@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
-def mk(request):
+@pytest.fixture(params=["oracle", pytest.param("cuda-per_match", marks=pytest.mark.gpu),
+                        pytest.param("cuda-per_body", marks=pytest.mark.gpu)])
+def mk(request, monkeypatch):
     if request.param == "oracle":
         from oracle import oracle as O
         O.build()
@@ -54,6 +55,8 @@ def mk(request):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from rsoccer_b200 import engine as E
+    # both kernel mappings (rs_create reads RS_PER_MATCH; unset = chosen by world size)
+    monkeypatch.setenv("RS_PER_MATCH", "1" if request.param.endswith("per_match") else "0")
     return lambda *a, **k: Sim("cuda", E, *a, **k)
 
 
