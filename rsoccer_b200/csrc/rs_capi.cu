@@ -39,7 +39,12 @@ template <int NB, int NY, int BS>
 __global__ void __launch_bounds__(BS, (448 / BS) > 0 ? (448 / BS) : 1)
 k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
     constexpr int R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
-    __shared__ __align__(128) float tile[BS * NOBS];
+    // one region per WARP: its contact scratch during the physics (2 x (R + 1) rows of 32 float4
+    // columns), then its 32 observation rows.  Nothing in it is ever touched by another warp.
+    constexpr int SCRATCH = 2 * (R + 1) * 32 * 4, WF = 32 * NOBS > SCRATCH ? 32 * NOBS : SCRATCH;
+    __shared__ __align__(128) float smem[BS / 32][WF];
+    float *const wtile = smem[threadIdx.x >> 5];
+    float4 *const cq = reinterpret_cast<float4 *>(wtile) + (threadIdx.x & 31), *const cp0 = cq + (R + 1) * 32;
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * BS;
     const int e = e0 + tid;
@@ -118,7 +123,11 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         }
 
         // ---- rsim.send_commands + get_frame, vss_gym_base.py:77-82
-        physics_step<RS_KIND_VSS, R>(P, s, d, live);
+#ifdef RS_O_CONST
+        physics_step<RS_KIND_VSS, R>(VssF0{}, s, d, live, cq, cp0, 32);
+#else
+        physics_step<RS_KIND_VSS, R>(P, s, d, live, cq, cp0, 32);
+#endif
 
         // ---- _calculate_reward_and_done, vss_gym.py:144-192
         float rew; bool goal = false;
@@ -159,10 +168,11 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         store_scene<R>(P, S, e, s);
         S.steps[e] = steps | ((has_prev ? 1 : 0) << 24);
         S.prev[e] = prev;
-        vss_obs<NB, NY>(P, s, tile + tid * NOBS);
+        __syncwarp(live);      // the rows below overlay the other lanes' contact scratch
+        vss_obs<NB, NY>(P, s, wtile + (tid & 31) * NOBS);
         step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
     }
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, wtile, wrows, NOBS);
 }
 
 
@@ -1156,7 +1166,6 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
     } else switch (w->block) {
         case 32: launch_step_kernel(k_vss_env_step<3, 3, 32>, (w->n + 31) / 32, 32, st, w->dp, S, A); break;
         case 128: launch_step_kernel(k_vss_env_step<3, 3, 128>, (w->n + 127) / 128, 128, st, w->dp, S, A); break;
-        case 256: launch_step_kernel(k_vss_env_step<3, 3, 256>, (w->n + 255) / 256, 256, st, w->dp, S, A); break;
         default: launch_step_kernel(k_vss_env_step<3, 3, 64>, (w->n + 63) / 64, 64, st, w->dp, S, A); break;
     }
     w->launches++; w->t++;

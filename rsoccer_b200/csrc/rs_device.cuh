@@ -14,6 +14,12 @@
 #include <stdint.h>
 #include "../../include/rs_spec.h"
 
+// Kernel-tuning experiment knobs (tools/variants.py builds one library per combination; the
+// product build defines none of them).
+#ifndef RS_X_SUBSTEPS
+#define RS_X_SUBSTEPS RS_SUBSTEPS
+#endif
+
 #define RS_PI_F 3.14159265358979323846f
 #define RS_DEG_F 57.29577951308232f
 
@@ -41,6 +47,31 @@ struct DevParams {
     float inv_max_pos, max_v, inv_max_v, inv_max_w_rad;  // obs w = clamp(omega[rad/s] * inv_max_w_rad)
     float sqrt_dt;
 };
+
+// Compile-time parameter block of the benchmarked world (VSS, field_type 0, 25 ms): the same
+// formulas as rs_params_fill / fill_dev_params evaluated by the compiler, so that the hot loop
+// sees immediates instead of constant-bank loads.  rs_capi.cu checks it field by field against
+// the run-time block before it selects a kernel built on it.
+struct VssF0 {
+    static constexpr double h_ = 0.025 / RS_SUBSTEPS, wb_ = 1.0 / 0.046, wr_ = 1.0 / 0.18;
+    static constexpr double br_ = 0.0375 + 0.0215, rr_ = 2.0 * 0.0375;
+    static constexpr int n_robots = 6;
+    static constexpr float h = (float)h_;
+    static constexpr float ball_r = (float)0.0215, rbt_r = (float)0.0375;
+    static constexpr float x_out = (float)(1.5 / 2 + 0.1), y_out = (float)(1.3 / 2);
+    static constexpr float wall_lx = (float)(1.5 / 2), wall_ly = (float)(0.4 / 2);
+    static constexpr float wb = (float)wb_, wr = (float)wr_, inv_wsum = (float)(1.0 / (wb_ + wr_));
+    static constexpr float fb = (float)(wb_ / (wb_ + wr_)), fr = (float)(wr_ / (wb_ + wr_));
+    static constexpr float e_ball_wall = (float)0.6, e_rbt_wall = (float)0.0, e_ball_rbt = (float)0.4, e_rbt_rbt = (float)0.0;
+    static constexpr float mu_ball_rbt = (float)0.3;
+    static constexpr float ball_decel_h = (float)(0.05 * 9.81 * h_);
+    static constexpr float rs_br = (float)br_, rs_br2 = (float)(br_ * br_), rs_rr = (float)rr_, rs_rr2 = (float)(rr_ * rr_);
+    static constexpr float acc_fwd_h = (float)(6.0 * h_), acc_lat_h = (float)(9.0 * h_), acc_ang_h = (float)(200.0 * h_);
+};
+__device__ __forceinline__ float wall_lx(const DevParams &P) { return P.box[0][0]; }
+__device__ __forceinline__ float wall_ly(const DevParams &P) { return P.box[0][1]; }
+__device__ __forceinline__ constexpr float wall_lx(const VssF0 &) { return VssF0::wall_lx; }
+__device__ __forceinline__ constexpr float wall_ly(const VssF0 &) { return VssF0::wall_ly; }
 
 template <int RT> struct Cap { static constexpr int v = RT > 0 ? RT : RS_MAX_ROBOTS; };
 
@@ -116,15 +147,15 @@ __device__ __forceinline__ bool touching(const DevParams &P, float rx, float ry,
 // as the generic closest-point test of the oracle for every reachable state (and for the
 // unreachable "centre inside the solid" state, which it resolves with the same
 // least-penetration face).
-template <int KIND>
-__device__ __forceinline__ void walls(const DevParams &P, float r, float e, float &x, float &y,
+template <int KIND, class PP>
+__device__ __forceinline__ void walls(const PP &P, float r, float e, float &x, float &y,
                                       float &vx, float &vy) {
     // mirror into the positive quadrant: multiply by sign(x) = flip the sign bit (exact)
     const uint32_t sgx = __float_as_uint(x) & 0x80000000u, sgy = __float_as_uint(y) & 0x80000000u;
     float ax = fabsf(x), ay = fabsf(y);
     float avx = __uint_as_float(__float_as_uint(vx) ^ sgx), avy = __uint_as_float(__float_as_uint(vy) ^ sgy);
-    if (KIND == RS_KIND_VSS) {
-        const float Lh = P.box[0][0], Gh = P.box[0][1];
+    if constexpr (KIND == RS_KIND_VSS) {
+        const float Lh = wall_lx(P), Gh = wall_ly(P);
         const bool inx = ax < Lh, iny = ay < Gh;
         const float dx = ax - Lh, dy = ay - Gh;
         if (__builtin_expect(inx && iny && dx > -r && dy > -r, 0)) {   // goal-post corner (rare)
@@ -182,8 +213,8 @@ __device__ __forceinline__ void walls(const DevParams &P, float r, float e, floa
 
 // robot <-> ball: detect on (rx, ry, rth) vs (bx, by); impulse on velocities, position
 // corrections accumulated into (cbx, cby) / (crx, cry)
-template <int KIND>
-__device__ __forceinline__ void ball_robot(const DevParams &P, float bx, float by, float &bvx,
+template <int KIND, class PP>
+__device__ __forceinline__ void ball_robot(const PP &P, float bx, float by, float &bvx,
                                            float &bvy, float rx, float ry, float rth, float &rvx,
                                            float &rvy, float rom, float &cbx, float &cby,
                                            float &crx, float &cry, bool &any) {
@@ -191,7 +222,7 @@ __device__ __forceinline__ void ball_robot(const DevParams &P, float bx, float b
     const float d2 = dx * dx + dy * dy;
     if (__builtin_expect(d2 >= P.rs_br2, 1)) return;
     float nx, ny, pen, rcx, rcy;
-    if (KIND == RS_KIND_VSS) {
+    if constexpr (KIND == RS_KIND_VSS) {
         float d = 0.0f; nx = 1.0f; ny = 0.0f;
         if (d2 > 1e-12f) { const float inv = rsqrtf(d2); nx = dx * inv; ny = dy * inv; d = d2 * inv; }
         pen = P.rs_br - d;
@@ -242,7 +273,8 @@ __device__ __forceinline__ void ball_robot(const DevParams &P, float bx, float b
     any = true;
 }
 
-__device__ __forceinline__ void robot_robot(const DevParams &P, float xi, float yi, float &vxi,
+template <class PP>
+__device__ __forceinline__ void robot_robot(const PP &P, float xi, float yi, float &vxi,
                                             float &vyi, float xj, float yj, float &vxj, float &vyj,
                                             float &cxi, float &cyi, float &cxj, float &cyj, bool &any) {
     const float dx = xj - xi, dy = yj - yi;
@@ -273,9 +305,9 @@ template <int R> __host__ __device__ constexpr int rr_pair_j(int k) {
     return i + 1 + k;
 }
 // warp-uniform jump to the register-static body of pair p in [LO, HI): a binary decision tree
-template <int KIND, int RT, int LO, int HI>
+template <int KIND, int RT, int LO, int HI, class PP>
 struct PairDispatch {
-    static __device__ __forceinline__ void run(const int p, const DevParams &P, Scene<RT> &s, float &cbx, float &cby,
+    static __device__ __forceinline__ void run(const int p, const PP &P, Scene<RT> &s, float &cbx, float &cby,
                                                float (&cx)[Cap<RT>::v], float (&cy)[Cap<RT>::v], bool &any) {
         if constexpr (HI - LO == 1) {
             if constexpr (LO < RT) {
@@ -287,11 +319,113 @@ struct PairDispatch {
             }
         } else {
             constexpr int MID = (LO + HI) / 2;
-            if (p < MID) PairDispatch<KIND, RT, LO, MID>::run(p, P, s, cbx, cby, cx, cy, any);
-            else PairDispatch<KIND, RT, MID, HI>::run(p, P, s, cbx, cby, cx, cy, any);
+            if (p < MID) PairDispatch<KIND, RT, LO, MID, PP>::run(p, P, s, cbx, cby, cx, cy, any);
+            else PairDispatch<KIND, RT, MID, HI, PP>::run(p, P, s, cbx, cby, cx, cy, any);
         }
     }
 };
+
+// ---- per-lane contact resolve through shared memory (VSS, lane-per-match kernels) ----
+// A contact is rare per lane but not per warp (see physics_step): with a register-static body
+// per pair, a warp of 32 matches executed ~2 of 21 different ~60-instruction bodies per
+// sub-step at 1-2 active lanes each -- 25 % of the step time, mostly dependent-latency and
+// instruction-cache misses (profiles/r1c_decomposition.txt).  Registers cannot be indexed by a
+// run-time pair number, shared memory can: a lane that has a contact publishes its scene to its
+// own column of a CTA scratch (no other lane ever touches that column: no barrier, no bank
+// conflict as the row pitch is a multiple of 128 B), resolves ITS OWN lowest pair with one
+// branch-free body for every pair type, repeats while it has pairs left (ascending =
+// lexicographic order, the oracle's Gauss-Seidel order), and reads the scene back.  Different
+// lanes resolve different pairs in the same pass.
+//   q[b]  = (x, y, vx, vy) of body b: receives impulses and position corrections
+//   p0[b] = (x, y, omega, -) at phase start: every contact of the phase is detected on these
+template <int R> __host__ __device__ constexpr uint64_t rr_table(bool second) {
+    uint64_t t = 0;
+    for (int k = 0; k < R * (R - 1) / 2; ++k) t |= (uint64_t)(second ? rr_pair_j<R>(k) : rr_pair_i<R>(k)) << (3 * k);
+    return t;
+}
+template <int RT, class PP>
+__device__ __forceinline__ void contacts_via_smem(const PP &P, Scene<RT> &s, uint32_t m, float4 *q, float4 *p0, const int pitch) {
+    static_assert(RT >= 1 && RT <= 7, "3-bit body indices, 21 robot pairs in 63 bits");
+    q[0] = make_float4(s.bx, s.by, s.bvx, s.bvy); p0[0] = make_float4(s.bx, s.by, 0.0f, 0.0f);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        q[(r + 1) * pitch] = make_float4(s.x[r], s.y[r], s.vx[r], s.vy[r]);
+        p0[(r + 1) * pitch] = make_float4(s.x[r], s.y[r], s.om[r], 0.0f);
+    }
+    constexpr uint64_t TI = rr_table<RT>(false), TJ = rr_table<RT>(true);
+    do {
+        const int p = __ffs((int)m) - 1;
+        m &= m - 1;
+        // normal points F -> S.  ball pairs: F = robot p, S = ball (body 0)
+        const bool ball = p < RT;
+        const int k3 = 3 * (p - RT);
+        const int F = ball ? p + 1 : 1 + (int)((TI >> k3) & 7u), S = ball ? 0 : 1 + (int)((TJ >> k3) & 7u);
+        const float4 pf = p0[F * pitch], ps = p0[S * pitch];
+        float4 qf = q[F * pitch], qs = q[S * pitch];
+        const float dx = ps.x - pf.x, dy = ps.y - pf.y;
+        const float d2 = dx * dx + dy * dy;
+        const float inv = rsqrtf(d2);
+        const bool ok = d2 > 1e-12f;
+        const float nx = ok ? dx * inv : 1.0f, ny = ok ? dy * inv : 0.0f, d = ok ? d2 * inv : 0.0f;
+        const float pen = (ball ? P.rs_br : P.rs_rr) - d;
+        const float rc = ball ? P.rbt_r : 0.0f;
+        const float rcx = nx * rc, rcy = ny * rc;
+        const float sx = qf.z - pf.z * rcy, sy = qf.w + pf.z * rcx;   // F's surface velocity at the contact
+        const float relx = qs.z - sx, rely = qs.w - sy;
+        const float vn = fminf(relx * nx + rely * ny, 0.0f);          // separating: every impulse below is +-0
+        // ball pair: Jn = -(1 + e) vn / (wb + wr), dv = Jn w n.  robot pair: equal masses, dv = -(1 + e) vn / 2 n
+        const float Jn = -(1.0f + (ball ? P.e_ball_rbt : P.e_rbt_rbt)) * vn * (ball ? P.inv_wsum : 0.5f);
+        const float wS = ball ? P.wb : 1.0f, wF = ball ? P.wr : 1.0f;
+        qs.z += Jn * wS * nx; qs.w += Jn * wS * ny;
+        qf.z -= Jn * wF * nx; qf.w -= Jn * wF * ny;
+        const float tx = -ny, ty = nx;
+        const float vt = relx * tx + rely * ty;
+        const float mu = ball ? P.mu_ball_rbt : 0.0f;
+        const float Jt = clampf(-vt * P.inv_wsum, -mu * Jn, mu * Jn);
+        qs.z += Jt * wS * tx; qs.w += Jt * wS * ty;
+        qf.z -= Jt * wF * tx; qf.w -= Jt * wF * ty;
+        const float gS = pen * (ball ? P.fb : 0.5f), gF = pen * (ball ? P.fr : 0.5f);
+        qs.x += gS * nx; qs.y += gS * ny;
+        qf.x -= gF * nx; qf.y -= gF * ny;
+        q[F * pitch] = qf; q[S * pitch] = qs;
+    } while (m);
+    {
+        const float4 b = q[0];
+        s.bx = b.x; s.by = b.y; s.bvx = b.z; s.bvy = b.w;
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const float4 b = q[(r + 1) * pitch];
+        s.x[r] = b.x; s.y[r] = b.y; s.vx[r] = b.z; s.vy[r] = b.w;
+    }
+}
+
+// register-static resolve: the masks are OR-reduced over the warp (REDUX) and the warp walks
+// the set bits in ascending (= lexicographic) order, jumping to the register-static body of
+// that pair; lanes without that contact fail the body's own distance test.
+template <int KIND, int RT, class PP>
+__device__ __forceinline__ void contacts_static(const PP &P, Scene<RT> &s, const uint32_t mask, const unsigned live) {
+    uint32_t wm = __reduce_or_sync(live, mask);
+#ifdef RS_X_NORESOLVE
+    if (wm == 0xdeadbeefu) {
+#else
+    if (wm) {
+#endif
+        float cbx = 0.0f, cby = 0.0f;
+        float cx[Cap<RT>::v], cy[Cap<RT>::v];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) { cx[r] = 0.0f; cy[r] = 0.0f; }
+        bool any = false;
+        do {
+            const int p = __ffs((int)wm) - 1;
+            wm &= wm - 1;
+            PairDispatch<KIND, RT, 0, RT + RT * (RT - 1) / 2, PP>::run(p, P, s, cbx, cby, cx, cy, any);
+        } while (wm);
+        s.bx += cbx; s.by += cby;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) { s.x[r] += cx[r]; s.y[r] += cy[r]; }
+    }
+}
 
 // commands -> drive targets.  VSS: cmd = (wl, wr) rad/s (rsim.py:100-101)
 __device__ __forceinline__ void vss_target(const DevParams &P, float wl, float wr, float &tf, float &tw) {
@@ -318,13 +452,15 @@ __device__ __forceinline__ void ssl_target(const DevParams &P, const float (&cmd
 }
 
 // ---------------------------------------------------------------- one control step
-template <int KIND, int RT>
-__device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, const Drive<RT> &d,
-                                             const unsigned live /* lanes of this warp that call */) {
+template <int KIND, int RT, class PP>
+__device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Drive<RT> &d,
+                                             const unsigned live /* lanes of this warp that call */,
+                                             float4 *cq = nullptr /* this lane's column of the contact scratch */,
+                                             float4 *cp0 = nullptr, const int cpitch = 0) {
     const int R = RT > 0 ? RT : P.n_robots;
     const float h = P.h;
     uint32_t kicked = 0;
-    if (KIND == RS_KIND_SSL) {
+    if constexpr (KIND == RS_KIND_SSL) {
         // kick: once per control step, robots in row order
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -338,18 +474,34 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
             }
         }
     }
+#ifdef RS_O_SCPIPE
+    float tsn[Cap<RT>::v], tcs[Cap<RT>::v];
+#pragma unroll
+    for (int r = 0; r < R; ++r) __sincosf(s.th[r], &tsn[r], &tcs[r]);
+#endif
 #pragma unroll 1
-    for (int k = 0; k < RS_SUBSTEPS; ++k) {
+    for (int k = 0; k < RS_X_SUBSTEPS; ++k) {
         int holder = -1; float hx = 0.0f, hy = 0.0f;
         // (a) drive, (b) dribbler latch
+#ifndef RS_X_NODRIVE
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float sn, cs;
+#ifdef RS_O_SCPIPE
+            sn = tsn[r]; cs = tcs[r];
+#else
             __sincosf(s.th[r], &sn, &cs);
+#endif
             float vf = cs * s.vx[r] + sn * s.vy[r], vl = -sn * s.vx[r] + cs * s.vy[r];
-            if (KIND == RS_KIND_VSS) {
+            if constexpr (KIND == RS_KIND_VSS) {
+#ifdef RS_O_CLAMP
+                // v + clamp(t - v, -a, a) == clamp(t, v - a, v + a): two independent adds, then min / max
+                vf = fmaxf(fminf(d.tf[r], vf + P.acc_fwd_h), vf - P.acc_fwd_h);
+                vl = fmaxf(fminf(d.tl[r], vl + P.acc_lat_h), vl - P.acc_lat_h);
+#else
                 vf += clampf(d.tf[r] - vf, -P.acc_fwd_h, P.acc_fwd_h);
                 vl += clampf(d.tl[r] - vl, -P.acc_lat_h, P.acc_lat_h);
+#endif
             } else {
                 const float df = d.tf[r] - vf, dl = d.tl[r] - vl;
                 const float n2 = df * df + dl * dl;
@@ -357,9 +509,13 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
                 if (n2 > P.acc_fwd_h * P.acc_fwd_h) sc = P.acc_fwd_h * rsqrtf(n2);
                 vf += df * sc; vl += dl * sc;
             }
+#ifdef RS_O_CLAMP
+            s.om[r] = fmaxf(fminf(d.tw[r], s.om[r] + P.acc_ang_h), s.om[r] - P.acc_ang_h);
+#else
             s.om[r] += clampf(d.tw[r] - s.om[r], -P.acc_ang_h, P.acc_ang_h);
+#endif
             s.vx[r] = cs * vf - sn * vl; s.vy[r] = sn * vf + cs * vl;
-            if (KIND == RS_KIND_SSL) {
+            if constexpr (KIND == RS_KIND_SSL) {
                 if (holder < 0 && ((d.drib >> r) & 1u) && !((kicked >> r) & 1u)) {
                     const float dx = s.bx - s.x[r], dy = s.by - s.y[r];
                     const float lx = cs * dx + sn * dy, ly = -sn * dx + cs * dy;
@@ -367,6 +523,7 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
                 }
             }
         }
+#endif
         // (c) ball rolling friction
         if (holder < 0) {
             const float sp2 = s.bvx * s.bvx + s.bvy * s.bvy;
@@ -377,7 +534,14 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             s.x[r] += s.vx[r] * h; s.y[r] += s.vy[r] * h;
+#ifdef RS_O_WRAP1
+            s.th[r] += s.om[r] * h;      // |omega| dt < 2 pi: wrapped once, after the last sub-step
+#else
             s.th[r] = wrap_pi(s.th[r] + s.om[r] * h);
+#endif
+#ifdef RS_O_SCPIPE
+            __sincosf(s.th[r], &tsn[r], &tcs[r]);   // for the next sub-step: MUFU latency hides under pairs + walls
+#endif
         }
         if (holder < 0) { s.bx += s.bvx * h; s.by += s.bvy * h; }
         else {
@@ -403,7 +567,11 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
         //      that pair; lanes without that contact fail the body's own distance test.
         // The hot path is thus branch-free and contiguous (no taken branch over a cold body
         // per pair: the kernel was instruction-fetch bound, profiles/r1_steady_final.txt).
-        if (RT > 0 && RT <= 7) {
+#ifdef RS_X_NOPAIRS
+        if constexpr (false) {
+#else
+        if constexpr (RT > 0 && RT <= 7) {
+#endif
             uint32_t mask = 0;
             {
                 int bit = 0;
@@ -423,23 +591,20 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
                     }
                 }
             }
-            uint32_t wm = __reduce_or_sync(live, mask);
-            if (wm) {
-                float cbx = 0.0f, cby = 0.0f;
-                float cx[Cap<RT>::v], cy[Cap<RT>::v];
-#pragma unroll
-                for (int r = 0; r < R; ++r) { cx[r] = 0.0f; cy[r] = 0.0f; }
-                bool any = false;
-                do {
-                    const int p = __ffs((int)wm) - 1;
-                    wm &= wm - 1;
-                    PairDispatch<KIND, RT, 0, RT + RT * (RT - 1) / 2>::run(p, P, s, cbx, cby, cx, cy, any);
-                } while (wm);
-                s.bx += cbx; s.by += cby;
-#pragma unroll
-                for (int r = 0; r < R; ++r) { s.x[r] += cx[r]; s.y[r] += cy[r]; }
+#ifdef RS_O_NOSMEMRESOLVE
+            contacts_static<KIND, RT>(P, s, mask, live);
+#else
+            if (KIND == RS_KIND_VSS && cpitch > 0) {     // constants once inlined
+                if (mask) contacts_via_smem<RT>(P, s, mask, cq, cp0, cpitch);
+            } else {
+                contacts_static<KIND, RT>(P, s, mask, live);
             }
+#endif
+#ifdef RS_X_NOPAIRS
+        } else if (false) {
+#else
         } else {
+#endif
             float cbx = 0.0f, cby = 0.0f;
             float cx[Cap<RT>::v], cy[Cap<RT>::v];
 #pragma unroll
@@ -463,10 +628,16 @@ __device__ __forceinline__ void physics_step(const DevParams &P, Scene<RT> &s, c
             }
         }
         // (f) walls
+#ifndef RS_X_NOWALLS
         walls<KIND>(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
 #pragma unroll
         for (int r = 0; r < R; ++r) walls<KIND>(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
+#endif
     }
+#ifdef RS_O_WRAP1
+#pragma unroll
+    for (int r = 0; r < R; ++r) s.th[r] = wrap_pi(s.th[r]);
+#endif
 }
 
 // ---------------------------------------------------------------- state I/O (SoA in HBM)

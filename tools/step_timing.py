@@ -33,29 +33,22 @@ TASKS = {
 }
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--task", default="vss", choices=sorted(TASKS))
-    ap.add_argument("--envs", type=int, default=65536)
-    ap.add_argument("--worlds", type=int, default=8)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=300, help="untimed steps per world")
-    ap.add_argument("--no-graph", action="store_true")
-    a = ap.parse_args()
-    kind, ft, nb, ny, task, adim = TASKS[a.task]
+def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=True):
+    """us per launch of one fused step of `task_name` at `envs` matches (see module docstring)."""
+    kind, ft, nb, ny, task, adim = TASKS[task_name]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     gen = torch.Generator(device="cpu").manual_seed(7)
     worlds, acts, outs = [], [], []
-    for m in range(a.worlds):
-        w = E.BatchedWorld(kind, ft, nb, ny, 25, a.envs, device=dev, seed=11, env_offset=m * a.envs)
+    for m in range(n_worlds):
+        w = E.BatchedWorld(kind, ft, nb, ny, 25, envs, device=dev, seed=11, env_offset=m * envs)
         if task is not None:
             w.task_reset(task)
-            acts.append((torch.rand(a.envs, adim, generator=gen) * 2 - 1).to(dev))
+            acts.append((torch.rand(envs, adim, generator=gen) * 2 - 1).to(dev))
             outs.append(w.alloc_outputs(task))
         else:
             w.task_reset(E.TASK_VSS_V0) if (kind == E.KIND_VSS and nb == 3 and ny == 3) else None
-            c = torch.rand(a.envs, nb + ny, w.cmd_dim, generator=gen) * 2 - 1
+            c = torch.rand(envs, nb + ny, w.cmd_dim, generator=gen) * 2 - 1
             if kind == E.KIND_VSS:
                 c = c * 40.0
             else:
@@ -66,7 +59,7 @@ def main():
         worlds.append(w)
 
     def step(i):
-        m = i % a.worlds
+        m = i % n_worlds
         if task is None:
             worlds[m].step(acts[m])
         elif task == E.TASK_VSS_V0:
@@ -74,21 +67,21 @@ def main():
         else:
             worlds[m].ssl_env_step(task, acts[m], out=outs[m])
 
-    M = a.worlds
+    M = n_worlds
     stream = torch.cuda.Stream(device=dev)
     graph = None
     with torch.cuda.stream(stream):
-        for i in range(a.warmup * M):
+        for i in range(warmup * M):
             step(i)
         stream.synchronize()
-        if not a.no_graph:
+        if use_graph:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 for i in range(M):
                     step(i)
             graph.replay()
             stream.synchronize()
-        reps = max(1, a.steps // M)
+        reps = max(1, steps // M)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for r in range(reps):
@@ -100,9 +93,24 @@ def main():
         e1.record(stream)
         stream.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (reps * M)
+    for w in worlds:
+        w.close()
+    return us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--task", default="vss", choices=sorted(TASKS))
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--worlds", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=300, help="untimed steps per world")
+    ap.add_argument("--no-graph", action="store_true")
+    a = ap.parse_args()
+    us = time_steps(a.task, a.envs, a.worlds, a.steps, a.warmup, not a.no_graph)
     mode = "per_match" if os.environ.get("RS_PER_MATCH", "") == "1" else ("per_body" if os.environ.get("RS_PER_MATCH", "") == "0" else "auto")
     print("TIMING task=%s envs=%d mode=%s pdl=%s graph=%d  %.2f us/step  %.1f Menv-steps/s" % (
-        a.task, a.envs, mode, os.environ.get("RS_PDL", "1"), graph is not None, us, a.envs / us))
+        a.task, a.envs, mode, os.environ.get("RS_PDL", "1"), not a.no_graph, us, a.envs / us))
 
 
 if __name__ == "__main__":
