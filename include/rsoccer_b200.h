@@ -163,6 +163,12 @@ int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto
 /* number of kernels this handle has launched so far (bench.py gpu_launches) */
 uint64_t rs_launch_count(const rs_world *w);
 
+/* which kernels step this world (diagnostics; the results do not depend on it):
+ *   bit 0  task kernels run one lane per BODY (else one lane per MATCH)
+ *   bit 1  rs_step runs one lane per BODY
+ *   bit 2  physics constants are compile-time immediates (VSS, field_type 0, 25 ms) */
+int rs_kernel_flags(const rs_world *w);
+
 #ifdef __cplusplus
 }
 #endif

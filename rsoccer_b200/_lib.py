@@ -32,7 +32,7 @@ SYMBOLS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_state_bytes", "rs_bind_state",
     "rs_layout", "rs_field_params", "rs_reset", "rs_step", "rs_get_state", "rs_set_raw",
     "rs_get_raw", "rs_get_t", "rs_set_t", "rs_sync_t", "rs_task_obs_dim", "rs_task_reset", "rs_vss_env_step",
-    "rs_ssl_env_step", "rs_vss_env_step_host", "rs_ssl_env_step_host", "rs_launch_count",
+    "rs_ssl_env_step", "rs_vss_env_step_host", "rs_ssl_env_step_host", "rs_launch_count", "rs_kernel_flags",
 )
 
 
@@ -101,6 +101,8 @@ def lib():
     L.rs_ssl_env_step_host.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
     L.rs_launch_count.restype = u64
     L.rs_launch_count.argtypes = [vp]
+    L.rs_kernel_flags.restype = i32
+    L.rs_kernel_flags.argtypes = [vp]
     _lib = L
     return L
 

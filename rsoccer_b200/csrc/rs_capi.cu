@@ -19,6 +19,13 @@ __global__ void k_set_ctr(uint32_t *ctr, int n_ctr, uint32_t t) {
     if (i < n_ctr) ctr[i] = t;
 }
 
+// resident CTAs per SM the headline kernel is compiled for: 448 threads = 14 warps per SM is what
+// 65 536 matches need (6.9 CTAs of 64), and it leaves ptxas 144 registers per thread
+#ifndef RS_VSS_THREADS
+#define RS_VSS_THREADS 448
+#endif
+#define RS_VSS_MINB(BS) ((RS_VSS_THREADS / (BS)) > 0 ? (RS_VSS_THREADS / (BS)) : 1)
+
 struct VssStepArgs {
     const float2 *actions;   // [N]
     const float *normals;    // [N][2(R-1)] or null
@@ -35,8 +42,8 @@ struct VssStepArgs {
 // VSSEnv.step for BS matches per CTA, one lane per match.  ONE launch = commands (agent +
 // OU noise), 5 physics sub-steps, reward/done/truncation, info accumulators, masked
 // auto-reset and the observation tile (leaves through a TMA bulk store).
-template <int NB, int NY, int BS>
-__global__ void __launch_bounds__(BS, (448 / BS) > 0 ? (448 / BS) : 1)
+template <int NB, int NY, int BS, bool F0 /* physics constants are VssF0's: immediates instead of constant-bank loads */>
+__global__ void __launch_bounds__(BS, RS_VSS_MINB(BS))
 k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
     constexpr int R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
     // one region per WARP: its contact scratch during the physics (2 x (R + 1) rows of 32 float4
@@ -123,11 +130,8 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         }
 
         // ---- rsim.send_commands + get_frame, vss_gym_base.py:77-82
-#ifdef RS_O_CONST
-        physics_step<RS_KIND_VSS, R>(VssF0{}, s, d, live, cq, cp0, 32);
-#else
-        physics_step<RS_KIND_VSS, R>(P, s, d, live, cq, cp0, 32);
-#endif
+        if constexpr (F0) physics_step<RS_KIND_VSS, R>(VssF0{}, s, d, live, cq, cp0, 32);
+        else physics_step<RS_KIND_VSS, R>(P, s, d, live, cq, cp0, 32);
 
         // ---- _calculate_reward_and_done, vss_gym.py:144-192
         float rew; bool goal = false;
@@ -152,27 +156,35 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 #pragma unroll
         for (int i = 0; i < RS_VSS_INFO; ++i) S.info[(size_t)i * S.np + e] = info[i];
 
-        if (A.auto_reset && (goal || tr)) {                         // rare: stays out of the hot registers
-            Scene<0> tmp;
-            vss_place<0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, t_now, RS_STREAM_AUTORESET), tmp);
-            s.bx = tmp.bx; s.by = tmp.by; s.bvx = 0.0f; s.bvy = 0.0f;
+        if (A.auto_reset) {
+            // rare (one match in ~6 000 per step) but on the critical path of the kernel: the
+            // whole warp draws the first 4 x wrows words of the ending match's placement stream
+            // at once, the ending lane then places from shared memory
+            unsigned need = __ballot_sync(live, goal || tr);
+            while (need) {
+                const int src = __ffs((int)need) - 1;
+                need &= need - 1;
+                const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+                const uint32_t env_src = A.env_offset + (uint32_t)(w0 + src);
+                const uint4 blk = philox4x32_10(make_uint4(env_src, t_now, RS_STREAM_AUTORESET, (uint32_t)(tid & 31)), key);
+                __syncwarp(live);
+                reinterpret_cast<uint4 *>(wtile)[tid & 31] = blk;
+                __syncwarp(live);
+                if ((tid & 31) == src) {
+                    PlaceStream g{reinterpret_cast<const uint32_t *>(wtile), wrows, key, env_src, t_now, 0};
+                    vss_place_stream<R>(P, g, s);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                s.x[r] = tmp.x[r]; s.y[r] = tmp.y[r]; s.th[r] = tmp.th[r];
-                s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+                    for (int r = 1; r < R; ++r) S.ou[(size_t)(r - 1) * S.np + e] = make_float2(0.0f, 0.0f);
+                    steps = 0; has_prev = false; prev = 0.0f;
+                }
             }
-#pragma unroll
-            for (int r = 1; r < R; ++r) S.ou[(size_t)(r - 1) * S.np + e] = make_float2(0.0f, 0.0f);
-            steps = 0; has_prev = false; prev = 0.0f;
         }
         store_scene<R>(P, S, e, s);
         S.steps[e] = steps | ((has_prev ? 1 : 0) << 24);
         S.prev[e] = prev;
-        __syncwarp(live);      // the rows below overlay the other lanes' contact scratch
-        vss_obs<NB, NY>(P, s, wtile + (tid & 31) * NOBS);
+        vss_obs<NB, NY>(P, s, A.obs + (size_t)e * NOBS);
         step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
     }
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, wtile, wrows, NOBS);
 }
 
 
@@ -655,7 +667,14 @@ k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__re
             if (drib) d.drib |= 1u << r;
         }
     }
-    physics_step<KIND, RT>(P, s, d, live);
+    if constexpr (KIND == RS_KIND_VSS && RT >= 1 && RT <= 7) {
+        // per-lane contact resolve through shared memory (rs_device.cuh): one region per warp
+        __shared__ __align__(16) float4 scratch[BS / 32][2 * (RT + 1) * 32];
+        float4 *const cq = scratch[threadIdx.x >> 5] + (threadIdx.x & 31);
+        physics_step<KIND, RT>(P, s, d, live, cq, cq + (RT + 1) * 32, 32);
+    } else {
+        physics_step<KIND, RT>(P, s, d, live);
+    }
     store_scene<RT>(P, S, e, s);
 }
 
@@ -812,6 +831,7 @@ struct rs_world {
     void *state;
     int64_t off[RS_ARR_COUNT];
     size_t state_bytes;
+    int f0;                  // 1: the physics constants equal VssF0 (kernels with immediates); RS_NO_PRESET=1 forces 0
     int block;               // CTA size of the step kernels
     int per_match;           // 1: one lane per MATCH kernels (rs_device.cuh); 0: one lane per BODY (rs_lanes.cuh); -1: by world size
     int lane_block;          // CTA size of the lane-per-body kernels
@@ -860,6 +880,22 @@ static void fill_dev_params(const rs_params &p, DevParams &d) {
     d.sqrt_dt = (float)sqrt(p.dt);
 }
 
+// Do the compile-time constants of VssF0 (rs_device.cuh) equal this world's run-time block?
+// Field by field, bit for bit: the kernels built on VssF0 are used only then.
+static bool matches_vss_f0(const DevParams &d) {
+    if (d.kind != RS_KIND_VSS || d.n_robots != VssF0::n_robots) return false;
+    const float a[] = {d.h, d.ball_r, d.rbt_r, d.x_out, d.y_out, d.box[0][0], d.box[0][1], d.wb, d.wr, d.inv_wsum, d.fb, d.fr,
+                       d.e_ball_wall, d.e_rbt_wall, d.e_ball_rbt, d.e_rbt_rbt, d.mu_ball_rbt, d.ball_decel_h,
+                       d.rs_br, d.rs_br2, d.rs_rr, d.rs_rr2, d.acc_fwd_h, d.acc_lat_h, d.acc_ang_h};
+    const float b[] = {VssF0::h, VssF0::ball_r, VssF0::rbt_r, VssF0::x_out, VssF0::y_out, VssF0::wall_lx, VssF0::wall_ly,
+                       VssF0::wb, VssF0::wr, VssF0::inv_wsum, VssF0::fb, VssF0::fr,
+                       VssF0::e_ball_wall, VssF0::e_rbt_wall, VssF0::e_ball_rbt, VssF0::e_rbt_rbt, VssF0::mu_ball_rbt,
+                       VssF0::ball_decel_h, VssF0::rs_br, VssF0::rs_br2, VssF0::rs_rr, VssF0::rs_rr2,
+                       VssF0::acc_fwd_h, VssF0::acc_lat_h, VssF0::acc_ang_h};
+    static_assert(sizeof(a) == sizeof(b), "one run-time field per VssF0 constant");
+    return memcmp(a, b, sizeof(a)) == 0;
+}
+
 static StatePtrs state_ptrs(const rs_world *w) {
     StatePtrs S;
     char *b = (char *)w->state;
@@ -876,10 +912,11 @@ static StatePtrs state_ptrs(const rs_world *w) {
 
 
 // Which mapping steps this world?  One lane per MATCH issues the fewest instructions but
-// needs n / 32 warps of ~120 registers to fill 592 SM sub-partitions; one lane per BODY
+// needs n / 32 warps of 128 registers to fill 592 SM sub-partitions; one lane per BODY
 // issues ~2.6x the instructions in 8x the warps.  Measured on B200 with
-// tools/step_timing.py, us per step, lane per body vs lane per match:
-//   VSS-v0 3 v 3        7.5 vs 12.0 @ 4 096    12.4 vs 12.7 @ 16 384    16.6 vs 14.5 @ 24 576    36.0 vs 21.8 @ 65 536
+// tools/step_timing.py, us per step, lane per body vs lane per match (round 1c: per-lane
+// contact resolve through shared memory, warp-cooperative auto-reset, immediates):
+//   VSS-v0 3 v 3        7.5 vs  8.0 @ 4 096     8.8 vs  8.2 @ 8 192    12.3 vs  8.6 @ 16 384    20.5 vs 12.1 @ 32 768   36.0 vs 18.3 @ 65 536
 //   SSL 1 v 6 task      9.8 vs 13.3 @ 4 096    14.9 vs 14.2 @ 16 384    37.6 vs 30.6 @ 65 536
 //   SSL 1 v 1 task      8.3 vs  6.5 @ 4 096    10.3 vs  7.0 @ 16 384    24.0 vs 11.9 @ 65 536
 //   rs_step SSL 1 v 6 (all seven robots driven)  8.6 vs 24.8 @ 4 096    36.1 vs 57.4 @ 65 536
@@ -890,7 +927,7 @@ static bool use_lane_per_body(const rs_world *w, bool task_kernel) {
     const int R = w->p.n_robots;
     if (R > 7) return true;
     if (R <= 2) return false;
-    if (w->p.kind == RS_KIND_VSS) return w->n < 20000;
+    if (w->p.kind == RS_KIND_VSS) return task_kernel ? w->n < 6000 : w->n < 20000;
     return task_kernel ? w->n < 14000 : true;
 }
 
@@ -976,6 +1013,8 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     if (const char *ls = getenv("RS_PER_MATCH")) w->per_match = atoi(ls) != 0;
     if (const char *ls = getenv("RS_PDL")) g_pdl = atoi(ls) != 0;
     if (const char *bs = getenv("RS_LANE_BLOCK")) { const int b = atoi(bs); if (b == 64 || b == 128 || b == 256) w->lane_block = b; }
+    w->f0 = matches_vss_f0(w->dp) ? 1 : 0;
+    if (const char *nv = getenv("RS_NO_PRESET")) { if (atoi(nv) == 1) w->f0 = 0; }
     if (const char *bs = getenv("RS_BLOCK")) { const int b = atoi(bs); if (b == 32 || b == 64 || b == 128 || b == 256) w->block = b; }
     w->n_ctr = w->np / RS_CTR_GROUP;
     if (cudaMalloc(&w->d_ctr, w->n_ctr * sizeof(uint32_t)) != cudaSuccess || cudaMemset(w->d_ctr, 0, w->n_ctr * sizeof(uint32_t)) != cudaSuccess) {
@@ -988,7 +1027,7 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
 
 int rs_destroy(rs_world *w) {
     if (!w) return RS_OK;
-    cudaFree(w->s_actions); cudaFree(w->s_obs); cudaFree(w->s_reward); cudaFree(w->s_done); cudaFree(w->s_trunc);
+    cudaFree(w->s_actions); cudaFree(w->s_obs);      // s_reward / s_done / s_trunc live inside s_obs's allocation
     cudaFree(w->d_ctr);
     delete w;
     return RS_OK;
@@ -1104,6 +1143,11 @@ int rs_sync_t(rs_world *w, void *stream) {
 }
 uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches : 0; }
 
+int rs_kernel_flags(const rs_world *w) {
+    if (!w) return 0;
+    return (use_lane_per_body(w, true) ? 1 : 0) | (use_lane_per_body(w, false) ? 2 : 0) | (w->f0 ? 4 : 0);
+}
+
 static void push_t(rs_world *w, cudaStream_t st) {
     if (!w->t_dirty) return;
     k_set_ctr<<<(w->n_ctr + 255) / 256, 256, 0, st>>>(w->d_ctr, w->n_ctr, (uint32_t)w->t);
@@ -1163,10 +1207,12 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
         if (w->lane_block == 256) launch_step_kernel(k_vss_env_step_lanes<256>, (w->n + 31) / 32, 256, st, w->dp, S, A);
         else if (w->lane_block == 64) launch_step_kernel(k_vss_env_step_lanes<64>, (w->n + 7) / 8, 64, st, w->dp, S, A);
         else launch_step_kernel(k_vss_env_step_lanes<128>, (w->n + 15) / 16, 128, st, w->dp, S, A);
-    } else switch (w->block) {
-        case 32: launch_step_kernel(k_vss_env_step<3, 3, 32>, (w->n + 31) / 32, 32, st, w->dp, S, A); break;
-        case 128: launch_step_kernel(k_vss_env_step<3, 3, 128>, (w->n + 127) / 128, 128, st, w->dp, S, A); break;
-        default: launch_step_kernel(k_vss_env_step<3, 3, 64>, (w->n + 63) / 64, 64, st, w->dp, S, A); break;
+    } else if (w->f0) switch (w->block) {
+        case 32: launch_step_kernel(k_vss_env_step<3, 3, 32, true>, (w->n + 31) / 32, 32, st, w->dp, S, A); break;
+        case 128: launch_step_kernel(k_vss_env_step<3, 3, 128, true>, (w->n + 127) / 128, 128, st, w->dp, S, A); break;
+        default: launch_step_kernel(k_vss_env_step<3, 3, 64, true>, (w->n + 63) / 64, 64, st, w->dp, S, A); break;
+    } else {
+        launch_step_kernel(k_vss_env_step<3, 3, 64, false>, (w->n + 63) / 64, 64, st, w->dp, S, A);
     }
     w->launches++; w->t++;
     CUDA_TRY(cudaGetLastError());
@@ -1214,25 +1260,36 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
     return RS_OK;
 }
 
+// Device staging of the *_host entry points.  The four outputs are ONE allocation laid out
+// [obs | reward | done | trunc]: a caller whose host buffers are laid out the same way (one
+// pinned block, BatchedWorld.alloc_host_outputs) gets a single device-to-host copy instead of
+// four (each copy costs ~8 us of fixed latency next to a 20 us kernel).
 static int ensure_scratch(rs_world *w, int act_dim, int obs_dim) {
     if (w->s_actions && w->s_act_dim == act_dim && w->s_obs_dim == obs_dim) return RS_OK;
-    cudaFree(w->s_actions); cudaFree(w->s_obs); cudaFree(w->s_reward); cudaFree(w->s_done); cudaFree(w->s_trunc);
+    cudaFree(w->s_actions); cudaFree(w->s_obs);
     w->s_actions = w->s_obs = w->s_reward = nullptr; w->s_done = w->s_trunc = nullptr;
-    CUDA_TRY(cudaMalloc(&w->s_actions, sizeof(float) * (size_t)w->n * act_dim));
-    CUDA_TRY(cudaMalloc(&w->s_obs, sizeof(float) * (size_t)w->n * obs_dim));
-    CUDA_TRY(cudaMalloc(&w->s_reward, sizeof(float) * (size_t)w->n));
-    CUDA_TRY(cudaMalloc(&w->s_done, (size_t)w->n));
-    CUDA_TRY(cudaMalloc(&w->s_trunc, (size_t)w->n));
+    const size_t n = (size_t)w->n;
+    CUDA_TRY(cudaMalloc(&w->s_actions, sizeof(float) * n * act_dim));
+    CUDA_TRY(cudaMalloc(&w->s_obs, sizeof(float) * n * obs_dim + sizeof(float) * n + 2 * n));
+    w->s_reward = w->s_obs + n * obs_dim;
+    w->s_done = reinterpret_cast<uint8_t *>(w->s_reward + n);
+    w->s_trunc = w->s_done + n;
     w->s_act_dim = act_dim; w->s_obs_dim = obs_dim;
     return RS_OK;
 }
 
 static int host_epilogue(rs_world *w, int obs_dim, float *h_obs, float *h_reward, uint8_t *h_done,
                          uint8_t *h_trunc, cudaStream_t st) {
-    CUDA_TRY(cudaMemcpyAsync(h_obs, w->s_obs, sizeof(float) * (size_t)w->n * obs_dim, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(h_reward, w->s_reward, sizeof(float) * (size_t)w->n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(h_done, w->s_done, (size_t)w->n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(h_trunc, w->s_trunc, (size_t)w->n, cudaMemcpyDeviceToHost, st));
+    const size_t n = (size_t)w->n, ob = sizeof(float) * n * obs_dim;
+    if (reinterpret_cast<char *>(h_reward) == reinterpret_cast<char *>(h_obs) + ob &&
+        h_done == reinterpret_cast<uint8_t *>(h_reward + n) && h_trunc == h_done + n) {
+        CUDA_TRY(cudaMemcpyAsync(h_obs, w->s_obs, ob + sizeof(float) * n + 2 * n, cudaMemcpyDeviceToHost, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(h_obs, w->s_obs, ob, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_reward, w->s_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_done, w->s_done, n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_trunc, w->s_trunc, n, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     return RS_OK;
 }

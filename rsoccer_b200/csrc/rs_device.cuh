@@ -211,6 +211,45 @@ __device__ __forceinline__ void walls(const PP &P, float r, float e, float &x, f
     vx = __uint_as_float(__float_as_uint(avx) ^ sgx); vy = __uint_as_float(__float_as_uint(avy) ^ sgy);
 }
 
+// VSS walls with the goal-post corner deferred: the axis limits of every body first (branch
+// free), then ONE branch for the whole scene if any body is within r of both faces of the
+// corner box.  Same result as walls<VSS>: a centre in the corner zone (|x| < Lh, |y| < Gh) is
+// below both axis limits before and after the radial push, so the order does not matter.
+template <class PP>
+__device__ __forceinline__ bool vss_walls_axes(const PP &P, float r, float e, float &x, float &y, float &vx, float &vy) {
+    const uint32_t sgx = __float_as_uint(x) & 0x80000000u, sgy = __float_as_uint(y) & 0x80000000u;
+    float ax = fabsf(x), ay = fabsf(y);
+    float avx = __uint_as_float(__float_as_uint(vx) ^ sgx), avy = __uint_as_float(__float_as_uint(vy) ^ sgy);
+    const float Lh = wall_lx(P), Gh = wall_ly(P);
+    const bool inx = ax < Lh, iny = ay < Gh;
+    const float dx = ax - Lh, dy = ay - Gh;
+    const bool interior = !inx && !iny, pick_y = dy < dx;
+    const bool box_x = !iny && !(interior && pick_y);
+    const bool box_y = !inx && !(interior && !pick_y);
+    const float xlim = (box_x ? Lh : P.x_out) - r, ylim = (box_y ? Gh : P.y_out) - r;
+    if (ax > xlim) { ax = xlim; avx = fminf(avx, -e * avx); }
+    if (ay > ylim) { ay = ylim; avy = fminf(avy, -e * avy); }
+    x = __uint_as_float(__float_as_uint(ax) | sgx); y = __uint_as_float(__float_as_uint(ay) | sgy);
+    vx = __uint_as_float(__float_as_uint(avx) ^ sgx); vy = __uint_as_float(__float_as_uint(avy) ^ sgy);
+    return inx && iny && dx > -r && dy > -r;
+}
+template <class PP>
+__device__ __forceinline__ void vss_walls_post(const PP &P, float r, float e, float &x, float &y, float &vx, float &vy) {
+    const float Lh = wall_lx(P), Gh = wall_ly(P);
+    const float sx = x < 0.0f ? -1.0f : 1.0f, sy = y < 0.0f ? -1.0f : 1.0f;
+    const float dx = fabsf(x) - Lh, dy = fabsf(y) - Gh;
+    if (!(dx < 0.0f && dy < 0.0f && dx > -r && dy > -r)) return;
+    const float d2 = dx * dx + dy * dy;
+    if (d2 < r * r) {
+        float nx = -1.0f, ny = 0.0f, pen = r;     // d2 <= 1e-12: oracle's interior rule, m = fxl = 0
+        if (d2 > 1e-12f) { const float inv = rsqrtf(d2); nx = dx * inv; ny = dy * inv; pen = r - d2 * inv; }
+        float ax = fabsf(x) + pen * nx, ay = fabsf(y) + pen * ny, avx = vx * sx, avy = vy * sy;
+        const float vn = avx * nx + avy * ny;
+        if (vn < 0.0f) { avx -= (1.0f + e) * vn * nx; avy -= (1.0f + e) * vn * ny; }
+        x = ax * sx; y = ay * sy; vx = avx * sx; vy = avy * sy;
+    }
+}
+
 // robot <-> ball: detect on (rx, ry, rth) vs (bx, by); impulse on velocities, position
 // corrections accumulated into (cbx, cby) / (crx, cry)
 template <int KIND, class PP>
@@ -474,11 +513,6 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
             }
         }
     }
-#ifdef RS_O_SCPIPE
-    float tsn[Cap<RT>::v], tcs[Cap<RT>::v];
-#pragma unroll
-    for (int r = 0; r < R; ++r) __sincosf(s.th[r], &tsn[r], &tcs[r]);
-#endif
 #pragma unroll 1
     for (int k = 0; k < RS_X_SUBSTEPS; ++k) {
         int holder = -1; float hx = 0.0f, hy = 0.0f;
@@ -487,21 +521,12 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float sn, cs;
-#ifdef RS_O_SCPIPE
-            sn = tsn[r]; cs = tcs[r];
-#else
             __sincosf(s.th[r], &sn, &cs);
-#endif
             float vf = cs * s.vx[r] + sn * s.vy[r], vl = -sn * s.vx[r] + cs * s.vy[r];
             if constexpr (KIND == RS_KIND_VSS) {
-#ifdef RS_O_CLAMP
                 // v + clamp(t - v, -a, a) == clamp(t, v - a, v + a): two independent adds, then min / max
                 vf = fmaxf(fminf(d.tf[r], vf + P.acc_fwd_h), vf - P.acc_fwd_h);
                 vl = fmaxf(fminf(d.tl[r], vl + P.acc_lat_h), vl - P.acc_lat_h);
-#else
-                vf += clampf(d.tf[r] - vf, -P.acc_fwd_h, P.acc_fwd_h);
-                vl += clampf(d.tl[r] - vl, -P.acc_lat_h, P.acc_lat_h);
-#endif
             } else {
                 const float df = d.tf[r] - vf, dl = d.tl[r] - vl;
                 const float n2 = df * df + dl * dl;
@@ -509,11 +534,7 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
                 if (n2 > P.acc_fwd_h * P.acc_fwd_h) sc = P.acc_fwd_h * rsqrtf(n2);
                 vf += df * sc; vl += dl * sc;
             }
-#ifdef RS_O_CLAMP
             s.om[r] = fmaxf(fminf(d.tw[r], s.om[r] + P.acc_ang_h), s.om[r] - P.acc_ang_h);
-#else
-            s.om[r] += clampf(d.tw[r] - s.om[r], -P.acc_ang_h, P.acc_ang_h);
-#endif
             s.vx[r] = cs * vf - sn * vl; s.vy[r] = sn * vf + cs * vl;
             if constexpr (KIND == RS_KIND_SSL) {
                 if (holder < 0 && ((d.drib >> r) & 1u) && !((kicked >> r) & 1u)) {
@@ -534,14 +555,7 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             s.x[r] += s.vx[r] * h; s.y[r] += s.vy[r] * h;
-#ifdef RS_O_WRAP1
             s.th[r] += s.om[r] * h;      // |omega| dt < 2 pi: wrapped once, after the last sub-step
-#else
-            s.th[r] = wrap_pi(s.th[r] + s.om[r] * h);
-#endif
-#ifdef RS_O_SCPIPE
-            __sincosf(s.th[r], &tsn[r], &tcs[r]);   // for the next sub-step: MUFU latency hides under pairs + walls
-#endif
         }
         if (holder < 0) { s.bx += s.bvx * h; s.by += s.bvy * h; }
         else {
@@ -557,49 +571,42 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
             }
         }
         // (e) pairs, lexicographic; contacts detected on the positions at phase start,
-        // velocity impulses applied sequentially, position corrections summed and applied
-        // afterwards.  A contact is rare per lane (~7 % of the matches have one at any time,
+        // velocity impulses applied sequentially, position corrections applied on top of them.
+        // A contact is rare per lane (~7 % of the matches have one at any time,
         // tools/contact_stats.py) but in a warp of 32 matches "some lane has one" holds for
-        // ~90 % of the sub-steps, spread over the pairs.  Up to 28 pairs (R <= 7):
-        //   1. detection is straight-line -- one mask bit per pair, no branch, full ILP;
-        //   2. the masks are OR-reduced over the warp (REDUX) and the warp walks the set bits
-        //      in ascending (= lexicographic) order, jumping to the register-static body of
-        //      that pair; lanes without that contact fail the body's own distance test.
-        // The hot path is thus branch-free and contiguous (no taken branch over a cold body
-        // per pair: the kernel was instruction-fetch bound, profiles/r1_steady_final.txt).
+        // ~95 % of the sub-steps, spread over the pairs.  Up to 28 pairs (R <= 7):
+        //   1. detection is straight-line: one FFMA pair and one funnel shift per pair (the sign
+        //      bit of d^2 - rs^2 is the mask bit), no compare, no branch, full ILP;
+        //   2. resolve: VSS task kernels -- each lane with a contact resolves its own pairs
+        //      through shared memory (contacts_via_smem); everything else -- the warp walks
+        //      the OR of the masks and jumps to register-static bodies (contacts_static).
 #ifdef RS_X_NOPAIRS
         if constexpr (false) {
 #else
         if constexpr (RT > 0 && RT <= 7) {
 #endif
-            uint32_t mask = 0;
-            {
-                int bit = 0;
+            // the sign bit of (d^2 - rs^2) enters the mask from the right, pairs visited in
+            // descending order so that pair 0 ends in bit 0; two chains for ILP
+            uint32_t mask = 0, mrr = 0;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float dx = s.bx - s.x[r], dy = s.by - s.y[r];
-                    if (dx * dx + dy * dy < P.rs_br2) mask |= 1u << bit;
-                    ++bit;
-                }
+            for (int i = R - 2; i >= 0; --i) {
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
-#pragma unroll
-                    for (int j = i + 1; j < R; ++j) {
-                        const float dx = s.x[j] - s.x[i], dy = s.y[j] - s.y[i];
-                        if (dx * dx + dy * dy < P.rs_rr2) mask |= 1u << bit;
-                        ++bit;
-                    }
+                for (int j = R - 1; j > i; --j) {
+                    const float dx = s.x[j] - s.x[i], dy = s.y[j] - s.y[i];
+                    mrr = __funnelshift_l(__float_as_uint(fmaf(dx, dx, fmaf(dy, dy, -P.rs_rr2))), mrr, 1);
                 }
             }
-#ifdef RS_O_NOSMEMRESOLVE
-            contacts_static<KIND, RT>(P, s, mask, live);
-#else
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+                const float dx = s.bx - s.x[r], dy = s.by - s.y[r];
+                mask = __funnelshift_l(__float_as_uint(fmaf(dx, dx, fmaf(dy, dy, -P.rs_br2))), mask, 1);
+            }
+            mask |= mrr << R;
             if (KIND == RS_KIND_VSS && cpitch > 0) {     // constants once inlined
                 if (mask) contacts_via_smem<RT>(P, s, mask, cq, cp0, cpitch);
             } else {
                 contacts_static<KIND, RT>(P, s, mask, live);
             }
-#endif
 #ifdef RS_X_NOPAIRS
         } else if (false) {
 #else
@@ -629,15 +636,20 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
         }
         // (f) walls
 #ifndef RS_X_NOWALLS
-        walls<KIND>(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
+        {
+            walls<KIND>(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
 #pragma unroll
-        for (int r = 0; r < R; ++r) walls<KIND>(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
+            for (int r = 0; r < R; ++r) walls<KIND>(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
+        }
 #endif
     }
-#ifdef RS_O_WRAP1
 #pragma unroll
-    for (int r = 0; r < R; ++r) s.th[r] = wrap_pi(s.th[r]);
-#endif
+    for (int r = 0; r < R; ++r) {
+        float a = s.th[r];
+        // more than one turn per control step needs time_step_ms > 100 at the motor limits
+        if (fabsf(a) > 3.0f * RS_PI_F) a = fmaf(-rintf(a * (0.5f / RS_PI_F)), 2.0f * RS_PI_F, a);
+        s.th[r] = wrap_pi(a);
+    }
 }
 
 // ---------------------------------------------------------------- state I/O (SoA in HBM)
@@ -712,16 +724,29 @@ __device__ __forceinline__ void warp_tile_store(float *gdst, const float *stile,
 // and no race: reader and writer of a copy are the same thread.
 //   GL = lanes per counter group = RS_CTR_GROUP x lanes per match (a divisor of 32).
 #define RS_CTR_GROUP 4
+// The counter words are the only input of the Philox / Box-Muller block, which is meant to
+// run under the latency of the state loads: they are loaded and stored with an L2
+// evict_last policy so that this 64 KB array survives in L2 between two steps of a world
+// while the state of other worlds streams through (an L2 hit returns ~1 us before HBM does).
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 template <int GL>
 __device__ __forceinline__ uint32_t step_counter_read(const uint32_t *ctr, const int e, const unsigned live = 0xffffffffu) {
     const int lane = threadIdx.x & 31;
     uint32_t t = 0u;
-    if ((lane & (GL - 1)) == 0) t = ctr[e / RS_CTR_GROUP];
+    if ((lane & (GL - 1)) == 0) {
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t) : "l"(ctr + e / RS_CTR_GROUP), "l"(l2_keep_policy()) : "memory");
+    }
     return __shfl_sync(live, t, lane & ~(GL - 1));      // a group's first lane is live whenever any of its lanes is
 }
 template <int GL>
 __device__ __forceinline__ void step_counter_bump(uint32_t *ctr, const int e, const uint32_t t) {
-    if (((threadIdx.x & 31) & (GL - 1)) == 0) ctr[e / RS_CTR_GROUP] = t + 1u;
+    if (((threadIdx.x & 31) & (GL - 1)) == 0) {
+        asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(ctr + e / RS_CTR_GROUP), "r"(t + 1u), "l"(l2_keep_policy()) : "memory");
+    }
 }
 
 // Programmatic dependent launch (sm_90+): a step kernel launched with the

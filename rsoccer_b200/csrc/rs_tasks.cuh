@@ -99,6 +99,50 @@ __device__ __noinline__ void vss_place(const DevParams &P, Rng g, Scene<RT> &s) 
         s.th[r] = wrap_pi(g.uniform(0.0f, 360.0f) * (1.0f / RS_DEG_F));
     }
 }
+// The same placement as vss_place, fed from a warp-generated block of the SAME Philox stream
+// and with the placed robots in (statically indexed) registers.  An episode end is rare per
+// lane but the kernel ends with its slowest warp, and ~10 matches of 65 536 end every step:
+// the scalar routine above (six dependent Philox calls, scene in local memory) was 1.1 us of
+// every 20 us step (profiles/r1c_decomposition.txt).  `buf` holds words 0 .. 4 navail - 1 of
+// the stream (counter word 3 = j, component = i & 3, exactly what Rng::next() walks through);
+// anything beyond is computed on the spot.
+__device__ __noinline__ uint32_t placement_word(uint2 key, uint32_t env, uint32_t t, int i) {
+    const uint4 u = philox4x32_10(make_uint4(env, t, RS_STREAM_AUTORESET, (uint32_t)(i >> 2)), key);
+    const int c = i & 3;
+    return c == 0 ? u.x : c == 1 ? u.y : c == 2 ? u.z : u.w;
+}
+struct PlaceStream {
+    const uint32_t *buf; int navail; uint2 key; uint32_t env, t; int i;
+    __device__ __forceinline__ float uniform(float a, float b) {
+        const uint32_t v = (i >> 2) < navail ? buf[i] : placement_word(key, env, t, i);
+        ++i;
+        return a + (b - a) * u01(v);
+    }
+};
+template <int R, class PP>
+__device__ __forceinline__ void vss_place_stream(const PP &P, PlaceStream g, Scene<R> &s) {
+    const float hl = P.half_len, hw = P.half_wid;
+    s.bx = g.uniform(-hl + 0.1f, hl - 0.1f); s.by = g.uniform(-hw + 0.1f, hw - 0.1f);
+    s.bvx = 0.0f; s.bvy = 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float x = 0.0f, y = 0.0f;
+#pragma unroll 1
+        for (int tries = 0; tries < 64; ++tries) {
+            x = g.uniform(-hl + 0.1f, hl - 0.1f); y = g.uniform(-hw + 0.1f, hw - 0.1f);
+            float dx = x - s.bx, dy = y - s.by;
+            bool ok = !(dx * dx + dy * dy < 0.01f);
+#pragma unroll
+            for (int k = 0; k < r; ++k) {
+                dx = x - s.x[k]; dy = y - s.y[k];
+                if (dx * dx + dy * dy < 0.01f) ok = false;
+            }
+            if (ok) break;
+        }
+        s.x[r] = x; s.y[r] = y; s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+        s.th[r] = wrap_pi(g.uniform(0.0f, 360.0f) * (1.0f / RS_DEG_F));
+    }
+}
 // static_defenders.py:214-254
 template <int RT>
 __device__ __noinline__ void ssl_sd_place(const DevParams &P, Rng g, Scene<RT> &s) {

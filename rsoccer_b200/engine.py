@@ -108,6 +108,11 @@ class BatchedWorld:
     def launches(self):
         return int(self.L.rs_launch_count(self.h))
 
+    @property
+    def kernel_flags(self):
+        """bit 0 / 1: task / rs_step kernels run one lane per body; bit 2: compile-time physics constants"""
+        return int(self.L.rs_kernel_flags(self.h))
+
     # ------------------------------------------------------------------ robosim surface
     def field_params(self):
         out = (C.c_double * 17)()
@@ -156,6 +161,15 @@ class BatchedWorld:
                 torch.empty(n, dtype=torch.float32, device=self.device),
                 torch.empty(n, dtype=torch.uint8, device=self.device),
                 torch.empty(n, dtype=torch.uint8, device=self.device))
+
+    def alloc_host_outputs(self, task):
+        """Pinned host (obs, reward, done, trunc) for the *_host steps, views of ONE block laid
+        out [obs | reward | done | trunc] so that the library moves them in a single copy."""
+        n, d = self.n, self.obs_dim(task)
+        blk = torch.empty(4 * n * d + 4 * n + 2 * n, dtype=torch.uint8).pin_memory()
+        o0, o1, o2 = 4 * n * d, 4 * n * d + 4 * n, 4 * n * d + 5 * n
+        return (blk[:o0].view(torch.float32).view(n, d), blk[o0:o1].view(torch.float32),
+                blk[o1:o2], blk[o2:])
 
     def task_reset(self, task, mask=None, obs=None):
         if obs is None:

@@ -78,10 +78,7 @@ class _FusedVecEnv:
         if self._pinned is None:
             n = self.num_envs
             self._pinned = (torch.empty(n, self.ACT_DIM, dtype=torch.float32).pin_memory(),
-                            torch.empty(n, self.obs_dim, dtype=torch.float32).pin_memory(),
-                            torch.empty(n, dtype=torch.float32).pin_memory(),
-                            torch.empty(n, dtype=torch.uint8).pin_memory(),
-                            torch.empty(n, dtype=torch.uint8).pin_memory())
+                            ) + self.world.alloc_host_outputs(self.TASK)      # one block -> one D2H copy
         a, o, r, d, t = self._pinned
         a.copy_(torch.as_tensor(actions_np, dtype=torch.float32).reshape(a.shape))
         self._step_host(a, o, r, d, t)

@@ -203,3 +203,33 @@ def test_checkpoint_restore_via_state_tensor(engine):
     w.state.copy_(snap); w.t = t
     again = [w.vss_env_step(a)[0].clone() for _ in range(5)]
     assert all(torch.equal(x, y) for x, y in zip(ref, again))
+
+
+def test_preset_kernel_is_selected_and_matches_the_generic_one(engine, monkeypatch):
+    """VSS field 0 at 25 ms steps on kernels whose physics constants are compile-time
+    immediates (rs_kernel_flags bit 2).  Same constants bit for bit (checked by the library
+    before it selects them), but the compiler contracts multiply-adds differently around
+    immediates, so against the run-time-constant kernels (RS_NO_PRESET=1) the results agree to
+    rounding, not to the bit: one step from identical state, 1e-5, auto-reset included; a
+    1-ulp flip of a contact decision may move a handful of rows further."""
+    E = engine
+    monkeypatch.setenv("RS_PER_MATCH", "1")
+    n = 1000
+    a = torch.rand(n, 2, device="cuda") * 2 - 1
+    w = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=3)
+    assert w.kernel_flags & 4 and not (w.kernel_flags & 1)
+    monkeypatch.setenv("RS_NO_PRESET", "1")
+    g = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=3)
+    assert not (g.kernel_flags & 4)
+    monkeypatch.delenv("RS_NO_PRESET")
+    assert not (E.BatchedWorld(0, 0, 3, 3, 20, 64, seed=3).kernel_flags & 4)
+    w.task_reset(E.TASK_VSS_V0)
+    bad = 0
+    for _ in range(40):
+        g.state.copy_(w.state); g.t = w.t
+        ow = w.vss_env_step(a, max_steps=15)
+        og = g.vss_env_step(a, max_steps=15)
+        row_ok = ((ow[0] - og[0]).abs().amax(dim=1) < 1e-5) & ((ow[1] - og[1]).abs() < 1e-5) & (ow[2] == og[2])
+        assert torch.equal(ow[3], og[3])
+        bad += int((~row_ok).sum())
+    assert bad <= 4, bad

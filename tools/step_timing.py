@@ -21,6 +21,8 @@ import torch  # noqa: E402
 
 from rsoccer_b200 import engine as E  # noqa: E402
 
+AUTO_RESET = os.environ.get("RS_NO_AUTORESET", "") != "1"
+
 TASKS = {
     "vss": (E.KIND_VSS, 0, 3, 3, E.TASK_VSS_V0, 2),
     "sd": (E.KIND_SSL, 2, 1, 6, E.TASK_SSL_STATIC_DEFENDERS_V0, 5),
@@ -63,7 +65,7 @@ def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=Tr
         if task is None:
             worlds[m].step(acts[m])
         elif task == E.TASK_VSS_V0:
-            worlds[m].vss_env_step(acts[m], out=outs[m])
+            worlds[m].vss_env_step(acts[m], out=outs[m], auto_reset=AUTO_RESET)
         else:
             worlds[m].ssl_env_step(task, acts[m], out=outs[m])
 
