@@ -37,6 +37,9 @@ struct VssStepArgs {
     uint64_t seed;
     uint32_t *ctr;           // world step counter t (Philox counter word 1), one copy per RS_CTR_GROUP matches
     uint32_t env_offset;
+#ifdef RS_X_STAGGER
+    int stagger_ns, stagger_mode;   // experiment: delay half of the CTAs (RS_STAGGER_NS, RS_STAGGER_MODE)
+#endif
 };
 
 // VSSEnv.step for BS matches per CTA, one lane per match.  ONE launch = commands (agent +
@@ -60,6 +63,13 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
     pdl_wait();
     pdl_release();
+#ifdef RS_X_STAGGER
+    if (A.stagger_ns > 0) {
+        const unsigned k = blockIdx.x / 148u;
+        const bool late = A.stagger_mode == 0 ? (k & 2u) != 0u : A.stagger_mode == 1 ? (k & 1u) != 0u : (blockIdx.x & 1u) != 0u;
+        if (late) __nanosleep((unsigned)A.stagger_ns);
+    }
+#endif
     if (e < S.n) {
         // ---- every global load of the step is issued first ...
         Scene<R> s;
@@ -1202,6 +1212,10 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
     cudaStream_t st = (cudaStream_t)stream;
     push_t(w, st);
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
+#ifdef RS_X_STAGGER
+    A.stagger_ns = getenv("RS_STAGGER_NS") ? atoi(getenv("RS_STAGGER_NS")) : 0;
+    A.stagger_mode = getenv("RS_STAGGER_MODE") ? atoi(getenv("RS_STAGGER_MODE")) : 0;
+#endif
     const StatePtrs S = state_ptrs(w);
     if (use_lane_per_body(w, true)) {
         if (w->lane_block == 256) launch_step_kernel(k_vss_env_step_lanes<256>, (w->n + 31) / 32, 256, st, w->dp, S, A);

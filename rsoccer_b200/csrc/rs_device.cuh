@@ -211,43 +211,46 @@ __device__ __forceinline__ void walls(const PP &P, float r, float e, float &x, f
     vx = __uint_as_float(__float_as_uint(avx) ^ sgx); vy = __uint_as_float(__float_as_uint(avy) ^ sgy);
 }
 
-// VSS walls with the goal-post corner deferred: the axis limits of every body first (branch
-// free), then ONE branch for the whole scene if any body is within r of both faces of the
-// corner box.  Same result as walls<VSS>: a centre in the corner zone (|x| < Lh, |y| < Gh) is
-// below both axis limits before and after the radial push, so the order does not matter.
+// VSS walls, lean form for the lane-per-match kernels (7 bodies x 5 sub-steps per step: the
+// largest single block of the sub-step loop).  No mirroring of the velocity, no predicate
+// chains: away from the goal post each axis has ONE limit chosen by the sign of the other
+// axis' distance to the corner box (|y| < Gh: the goal mouth band lets x run to the back of
+// the goal; |x| >= Lh: inside the goal y stays within the mouth), the position is clamped with
+// min/max and the velocity component is reflected only if it points outward.  A centre within
+// r of BOTH faces of the corner box -- the rounded post, or (unreachable) inside the solid --
+// takes the one branch.  Same decisions and arithmetic as walls<VSS>() above.
 template <class PP>
-__device__ __forceinline__ bool vss_walls_axes(const PP &P, float r, float e, float &x, float &y, float &vx, float &vy) {
-    const uint32_t sgx = __float_as_uint(x) & 0x80000000u, sgy = __float_as_uint(y) & 0x80000000u;
-    float ax = fabsf(x), ay = fabsf(y);
-    float avx = __uint_as_float(__float_as_uint(vx) ^ sgx), avy = __uint_as_float(__float_as_uint(vy) ^ sgy);
-    const float Lh = wall_lx(P), Gh = wall_ly(P);
-    const bool inx = ax < Lh, iny = ay < Gh;
-    const float dx = ax - Lh, dy = ay - Gh;
-    const bool interior = !inx && !iny, pick_y = dy < dx;
-    const bool box_x = !iny && !(interior && pick_y);
-    const bool box_y = !inx && !(interior && !pick_y);
-    const float xlim = (box_x ? Lh : P.x_out) - r, ylim = (box_y ? Gh : P.y_out) - r;
-    if (ax > xlim) { ax = xlim; avx = fminf(avx, -e * avx); }
-    if (ay > ylim) { ay = ylim; avy = fminf(avy, -e * avy); }
-    x = __uint_as_float(__float_as_uint(ax) | sgx); y = __uint_as_float(__float_as_uint(ay) | sgy);
-    vx = __uint_as_float(__float_as_uint(avx) ^ sgx); vy = __uint_as_float(__float_as_uint(avy) ^ sgy);
-    return inx && iny && dx > -r && dy > -r;
-}
+__device__ __forceinline__ float wall_bounce(const PP &, const float e, const float v) { return e == 0.0f ? 0.0f : -e * v; }
 template <class PP>
-__device__ __forceinline__ void vss_walls_post(const PP &P, float r, float e, float &x, float &y, float &vx, float &vy) {
+__device__ __forceinline__ void vss_walls(const PP &P, const float r, const float e, float &x, float &y, float &vx, float &vy) {
     const float Lh = wall_lx(P), Gh = wall_ly(P);
-    const float sx = x < 0.0f ? -1.0f : 1.0f, sy = y < 0.0f ? -1.0f : 1.0f;
+    const float XO = P.x_out - r, XL = Lh - r, YO = P.y_out - r, YL = Gh - r;      // loop invariants / immediates
     const float dx = fabsf(x) - Lh, dy = fabsf(y) - Gh;
-    if (!(dx < 0.0f && dy < 0.0f && dx > -r && dy > -r)) return;
-    const float d2 = dx * dx + dy * dy;
-    if (d2 < r * r) {
-        float nx = -1.0f, ny = 0.0f, pen = r;     // d2 <= 1e-12: oracle's interior rule, m = fxl = 0
-        if (d2 > 1e-12f) { const float inv = rsqrtf(d2); nx = dx * inv; ny = dy * inv; pen = r - d2 * inv; }
-        float ax = fabsf(x) + pen * nx, ay = fabsf(y) + pen * ny, avx = vx * sx, avy = vy * sy;
-        const float vn = avx * nx + avy * ny;
-        if (vn < 0.0f) { avx -= (1.0f + e) * vn * nx; avy -= (1.0f + e) * vn * ny; }
-        x = ax * sx; y = ay * sy; vx = avx * sx; vy = avy * sy;
+    float xlim = dy < 0.0f ? XO : XL, ylim = dx < 0.0f ? YO : YL;
+    // both within r of a face AND on the same side of both faces (a robot leaning on the end
+    // wall is within r of both, but outside one and inside the other: no branch for it)
+    if (__builtin_expect(dx > -r && dy > -r && dx * dy >= 0.0f, 0)) {
+        if (dx < 0.0f && dy < 0.0f) {
+            const float d2 = dx * dx + dy * dy;
+            if (d2 < r * r) {                             // rounded goal-post corner, in the mirrored quadrant
+                const float sx = copysignf(1.0f, x), sy = copysignf(1.0f, y);
+                float nx = -1.0f, ny = 0.0f, pen = r;     // d2 <= 1e-12: oracle's interior rule, m = fxl = 0
+                if (d2 > 1e-12f) { const float inv = rsqrtf(d2); nx = dx * inv; ny = dy * inv; pen = r - d2 * inv; }
+                float avx = vx * sx, avy = vy * sy;
+                const float vn = avx * nx + avy * ny;
+                if (vn < 0.0f) { avx -= (1.0f + e) * vn * nx; avy -= (1.0f + e) * vn * ny; }
+                x = (fabsf(x) + pen * nx) * sx; y = (fabsf(y) + pen * ny) * sy;
+                vx = avx * sx; vy = avy * sy;
+            }
+        } else if (dx >= 0.0f && dy >= 0.0f) {            // inside the solid: least-penetration face only
+            if (dy < dx) xlim = XO; else ylim = YO;
+        }
     }
+    const float ox = vx * x, oy = vy * y;                 // > 0: moving outward
+    const bool hx = fabsf(x) > xlim, hy = fabsf(y) > ylim;
+    x = fmaxf(fminf(x, xlim), -xlim); y = fmaxf(fminf(y, ylim), -ylim);
+    if (hx && ox > 0.0f) vx = wall_bounce(P, e, vx);
+    if (hy && oy > 0.0f) vy = wall_bounce(P, e, vy);
 }
 
 // robot <-> ball: detect on (rx, ry, rth) vs (bx, by); impulse on velocities, position
@@ -636,7 +639,11 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
         }
         // (f) walls
 #ifndef RS_X_NOWALLS
-        {
+        if constexpr (KIND == RS_KIND_VSS) {
+            vss_walls(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
+#pragma unroll
+            for (int r = 0; r < R; ++r) vss_walls(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
+        } else {
             walls<KIND>(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
 #pragma unroll
             for (int r = 0; r < R; ++r) walls<KIND>(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);

@@ -35,7 +35,7 @@ TASKS = {
 }
 
 
-def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=True):
+def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=True, graph_steps=0):
     """us per launch of one fused step of `task_name` at `envs` matches (see module docstring)."""
     kind, ft, nb, ny, task, adim = TASKS[task_name]
     dev = torch.device("cuda", 0)
@@ -69,7 +69,7 @@ def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=Tr
         else:
             worlds[m].ssl_env_step(task, acts[m], out=outs[m])
 
-    M = n_worlds
+    M = max(n_worlds, graph_steps)          # steps per captured graph (a multiple of the world count)
     stream = torch.cuda.Stream(device=dev)
     graph = None
     with torch.cuda.stream(stream):

@@ -65,7 +65,7 @@ def run(argv):
             res = []
             for n in [int(x) for x in a.sizes.split(",")]:
                 try:
-                    res.append("%d:%.2f" % (n, T.time_steps(a.task, n, n_worlds=a.worlds, steps=a.steps)))
+                    res.append("%d:%.2f" % (n, T.time_steps(a.task, n, n_worlds=a.worlds, steps=a.steps, graph_steps=8)))
                 except Exception as ex:  # noqa: BLE001
                     res.append("%d:ERR(%s)" % (n, str(ex)[:80]))
             line = "%-28s task=%s mode=%s worlds=%d %s  %s" % (f[4:-3], a.task, a.mode, a.worlds, a.env, "  ".join(res))
