@@ -109,14 +109,6 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
             }
         }
 
-        int steps = st & 0xFFFFFF;
-        bool has_prev = (st >> 24) & 1;
-        if (steps == 0) {
-#pragma unroll
-            for (int i = 0; i < RS_VSS_INFO; ++i) info[i] = 0.0f;
-        }
-        steps += 1;                                                 // vss_gym_base.py:73
-
         // ---- _get_commands, vss_gym.py:119-142
         Drive<R> d;
         d.drib = 0;
@@ -142,6 +134,15 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         // ---- rsim.send_commands + get_frame, vss_gym_base.py:77-82
         if constexpr (F0) physics_step<RS_KIND_VSS, R>(VssF0{}, s, d, live, cq, cp0, 32);
         else physics_step<RS_KIND_VSS, R>(P, s, d, live, cq, cp0, 32);
+
+        // ---- the task words (loaded at the top) are first needed here, after the physics
+        int steps = st & 0xFFFFFF;
+        bool has_prev = (st >> 24) & 1;
+        if (steps == 0) {
+#pragma unroll
+            for (int i = 0; i < RS_VSS_INFO; ++i) info[i] = 0.0f;
+        }
+        steps += 1;                                                 // vss_gym_base.py:73
 
         // ---- _calculate_reward_and_done, vss_gym.py:144-192
         float rew; bool goal = false;
@@ -192,8 +193,20 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         store_scene<R>(P, S, e, s);
         S.steps[e] = steps | ((has_prev ? 1 : 0) << 24);
         S.prev[e] = prev;
-        vss_obs<NB, NY>(P, s, A.obs + (size_t)e * NOBS);
+        __syncwarp(live);      // the rows below overlay the other lanes' contact scratch
+        vss_obs<NB, NY>(P, s, wtile + (tid & 31) * NOBS);
         step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
+    }
+    // the rows of a warp are one contiguous span of global memory: every lane of the warp (live
+    // or not) ships 16-byte pieces of it, coalesced -- half the L2 write sectors of row-per-lane
+    // stores, and unlike a TMA bulk store nothing to wait for before the warp exits
+    __syncwarp();
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(wtile);
+        float4 *dst = reinterpret_cast<float4 *>(A.obs + (size_t)w0 * NOBS);
+        const int total = wrows * (NOBS / 4);
+#pragma unroll
+        for (int i = 0; i < NOBS / 4; ++i) { const int k = i * 32 + (tid & 31); if (k < total) dst[k] = src[k]; }
     }
 }
 
@@ -1205,6 +1218,7 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
     if (!d_actions || !d_obs || !d_reward || !d_done || !d_trunc)
         return fail(RS_E_INVALID, "rs_vss_env_step: null argument");
     if (max_steps < 1 || max_steps > 0xFFFFFF) return fail(RS_E_INVALID, "rs_vss_env_step: bad max_steps");
+    if (((uintptr_t)d_obs & 15u) || ((uintptr_t)d_actions & 7u)) return fail(RS_E_INVALID, "rs_vss_env_step: obs must be 16-byte and actions 8-byte aligned");
     VssStepArgs A;
     A.actions = reinterpret_cast<const float2 *>(d_actions); A.normals = d_normals;
     A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.trunc = d_trunc; A.cmds_out = d_cmds_out;

@@ -1,4 +1,4 @@
-mkdir -p gpurun_out; rm -f gpurun_out/variants.txt
-python tools/variants.py run --task vss --sizes 4096,16384,32768,65536,262144 --mode 1 > gpurun_out/run11.log 2>&1
-RS_LIB=build/variants/lib_wall4.so timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 >> gpurun_out/run11.log
-cat gpurun_out/run11.log
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/run13.log
+for n in 4096 65536; do RS_PER_MATCH=1 python tools/step_timing.py --task vss --envs $n >> gpurun_out/run13.log 2>&1; done
+cat gpurun_out/run13.log
