@@ -267,6 +267,14 @@ static inline void rs_params_field(const rs_params *p, double out[RS_FIELD_KEYS]
 #define RS_TASK_VSS 0
 #define RS_TASK_SSL_STATIC_DEFENDERS 1
 #define RS_TASK_SSL_CONTESTED_POSSESSION 2
+#define RS_TASK_SSL_DRIBBLING 3        /* SSLDribbling-v0: 1 blue + 4 yellow, dribbling.py:47-49 [REF] */
+#define RS_TASK_SSL_PASS_ENDURANCE 4   /* SSLPassEndurance-v0: 2 blue, pass_endurance.py:46-52 [REF] */
+#define RS_DRIB_ACT 4                  /* dribbling.py:50-51 [REF] */
+#define RS_DRIB_OBS 21                 /* 5 + 8 nb + 2 ny, dribbling.py:53 [REF] */
+#define RS_DRIB_MAX_STEPS 4800         /* rsoccer_gym/__init__.py:17 [REF] */
+#define RS_PASS_ACT 3                  /* pass_endurance.py:53 [REF] */
+#define RS_PASS_OBS 16                 /* 4 + 6 nb, pass_endurance.py:55 [REF] */
+#define RS_PASS_MAX_STEPS 1200         /* rsoccer_gym/__init__.py:29 [REF] */
 
 /* Philox stream ids (counter word 2) */
 #define RS_STREAM_OU 0u

@@ -18,6 +18,13 @@ _LIB_PATH = os.path.join(_HERE, "librs_oracle.so")
 
 KIND_VSS, KIND_SSL = 0, 1
 TASK_VSS, TASK_SSL_STATIC_DEFENDERS, TASK_SSL_CONTESTED_POSSESSION = 0, 1, 2
+TASK_SSL_DRIBBLING, TASK_SSL_PASS_ENDURANCE = 3, 4
+TASK_ACT = {0: 2, 1: 5, 2: 5, 3: 4, 4: 3}
+
+
+def task_obs_dim(task, nb, ny):
+    return {0: 4 + 7 * nb + 5 * ny, 3: 5 + 8 * nb + 2 * ny, 4: 4 + 6 * nb}.get(task, 4 + 8 * nb + 2 * ny)
+
 INFO_W = 9
 
 FIELD_KEYS = (
@@ -67,6 +74,7 @@ def lib():
         L.orc_task_reset.argtypes = [vp, i32, vp]
         L.orc_vss_env_step.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
         L.orc_ssl_env_step.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
+        L.orc_ssl_hw_env_step.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
         L.orc_task_obs.argtypes = [vp, i32, vp]
         L.orc_philox.argtypes = [vp, vp, vp]
         L.orc_max_threads.restype = i32
@@ -185,8 +193,7 @@ class OracleWorld:
         self.L.orc_task_reset(self.h, task, _p(m))
 
     def task_obs(self, task):
-        n_obs = (4 + 7 * self.nb + 5 * self.ny) if task == TASK_VSS else (4 + 8 * self.nb + 2 * self.ny)
-        obs = np.zeros((self.n, n_obs))
+        obs = np.zeros((self.n, task_obs_dim(task, self.nb, self.ny)))
         self.L.orc_task_obs(self.h, task, _p(obs))
         return obs
 
@@ -204,12 +211,13 @@ class OracleWorld:
         return (obs, rew, done, trunc, cmds) if want_cmds else (obs, rew, done, trunc)
 
     def ssl_env_step(self, task, actions, auto_reset=True, max_steps=1000, want_cmds=False):
-        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 5)
-        obs = np.zeros((self.n, 4 + 8 * self.nb + 2 * self.ny))
+        """static defenders / contested possession (5 actions), dribbling (4), pass endurance (3)"""
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, TASK_ACT[task])
+        obs = np.zeros((self.n, task_obs_dim(task, self.nb, self.ny)))
         rew = np.zeros(self.n)
         done = np.zeros(self.n, dtype=np.uint8)
         trunc = np.zeros(self.n, dtype=np.uint8)
         cmds = np.zeros((self.n, self.R, 8)) if want_cmds else None
-        self.L.orc_ssl_env_step(self.h, task, _p(a), int(auto_reset), max_steps, _p(obs), _p(rew),
-                                _p(done), _p(trunc), _p(cmds))
+        fn = self.L.orc_ssl_hw_env_step if task in (TASK_SSL_DRIBBLING, TASK_SSL_PASS_ENDURANCE) else self.L.orc_ssl_env_step
+        fn(self.h, task, _p(a), int(auto_reset), max_steps, _p(obs), _p(rew), _p(done), _p(trunc), _p(cmds))
         return (obs, rew, done, trunc, cmds) if want_cmds else (obs, rew, done, trunc)

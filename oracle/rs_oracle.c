@@ -641,12 +641,40 @@ static void ssl_cp_place(const rs_params *p, o_rng *g, o_ball *b, o_robot *rb) {
     }
 }
 
+/* dribbling.py:187-202: fixed course, robot at the origin facing -x with the ball in its mouth */
+static void ssl_drib_place(const rs_params *p, o_rng *g, o_ball *b, o_robot *rb) {
+    (void)g;
+    b->x = -0.1; b->y = 0.0; b->vx = b->vy = 0.0;
+    for (int r = 0; r < p->n_robots; ++r) {
+        rb[r].x = r == 0 ? 0.0 : -0.5 * r; rb[r].y = 0.0; rb[r].th = PI;
+        rb[r].vx = rb[r].vy = rb[r].om = 0.0;
+    }
+}
+/* pass_endurance.py:152-181: ball anywhere in [-1.5, 1.5]^2, the shooter 0.115 m behind it facing
+ * the ball along y, the receiver mirrored in y at least 1 m away in x, facing the shooter */
+static void ssl_pass_place(const rs_params *p, o_rng *g, o_ball *b, o_robot *rb) {
+    (void)p;
+    b->x = rng_uniform(g, -1.5, 1.5); b->y = rng_uniform(g, 1.5, -1.5); b->vx = b->vy = 0.0;
+    const double factor = b->y < 0.0 ? -1.0 : 1.0;
+    rb[0].x = b->x; rb[0].y = b->y + 0.115 * factor; rb[0].th = factor > 0.0 ? -0.5 * PI : 0.5 * PI;
+    double rx = 0.0;
+    for (int tries = 0; tries < 64; ++tries) {
+        rx = rng_uniform(g, -1.5, 1.5);
+        if (!(fabs(rx - b->x) < 1.0)) break;
+    }
+    rb[1].x = rx; rb[1].y = -b->y;
+    rb[1].th = wrap_pi(atan2(rb[1].y - rb[0].y, rb[1].x - rb[0].x) + PI);
+    for (int r = 0; r < 2; ++r) rb[r].vx = rb[r].vy = rb[r].om = 0.0;
+}
+
 static void place(const orc_world *w, int task, int e, uint32_t stream) {
     o_rng g;
     rng_init(&g, w->seed, (uint64_t)(w->env_offset + e), w->t, stream);
     const int R = w->p.n_robots;
     if (task == RS_TASK_VSS) vss_place(&w->p, &g, &w->ball[e], &w->rob[(size_t)e * R]);
     else if (task == RS_TASK_SSL_STATIC_DEFENDERS) ssl_sd_place(&w->p, &g, &w->ball[e], &w->rob[(size_t)e * R]);
+    else if (task == RS_TASK_SSL_DRIBBLING) ssl_drib_place(&w->p, &g, &w->ball[e], &w->rob[(size_t)e * R]);
+    else if (task == RS_TASK_SSL_PASS_ENDURANCE) ssl_pass_place(&w->p, &g, &w->ball[e], &w->rob[(size_t)e * R]);
     else ssl_cp_place(&w->p, &g, &w->ball[e], &w->rob[(size_t)e * R]);
 }
 
@@ -817,12 +845,155 @@ void orc_ssl_env_step(orc_world *w, int task, const float *actions, int auto_res
     w->t++;
 }
 
+/* ---- SSLDribbling-v0 / SSLPassEndurance-v0 (ssl_hw_challenge/dribbling.py, pass_endurance.py) ----
+ * The per-episode counter of each task (dribbling: checkpoints_count; pass endurance:
+ * stopped_steps) lives in prev_pot[e].  info[0..1] of pass endurance = reward_shaping_total
+ * {reversed_dist, ball_grad} (pass_endurance.py:113-114); its holding_steps is never incremented
+ * by the reference (initialised :56, reset :92, only compared :121), so `> 15` never fires.   */
+static void ssl_hw_obs(const rs_params *p, int task, const o_ball *b, const o_robot *rb, double counter,
+                       double *o, double *mg) {
+    const double mp = max_pos_of(p), max_v = 2.5, max_w = 10.0;       /* dribbling.py:66-67, pass_endurance.py:73-74 */
+    int k = 0;
+    if (task == RS_TASK_SSL_DRIBBLING) {                               /* dribbling.py:75-105 */
+        o[k++] = ((counter / 6) * 2) - 1;
+        o[k++] = nrm(b->x, mp); o[k++] = nrm(b->y, mp); o[k++] = nrm(b->vx, max_v); o[k++] = nrm(b->vy, max_v);
+        for (int r = 0; r < p->n_blue; ++r) {
+            o[k++] = nrm(rb[r].x, mp); o[k++] = nrm(rb[r].y, mp);
+            o[k++] = sin(rb[r].th); o[k++] = cos(rb[r].th);
+            o[k++] = nrm(rb[r].vx, max_v); o[k++] = nrm(rb[r].vy, max_v);
+            o[k++] = nrm(rb[r].om * DEG, max_w);
+            o[k++] = touching(p, &rb[r], b, mg) ? 1.0 : -1.0;
+        }
+        for (int r = p->n_blue; r < p->n_robots; ++r) { o[k++] = nrm(rb[r].x, mp); o[k++] = nrm(rb[r].y, mp); }
+    } else {                                                           /* pass_endurance.py:78-90 */
+        o[k++] = nrm(b->x, mp); o[k++] = nrm(b->y, mp); o[k++] = nrm(b->vx, max_v); o[k++] = nrm(b->vy, max_v);
+        for (int r = 0; r < p->n_blue; ++r) {
+            o[k++] = nrm(rb[r].x, mp); o[k++] = nrm(rb[r].y, mp);
+            o[k++] = sin(rb[r].th); o[k++] = cos(rb[r].th);
+            o[k++] = nrm(rb[r].om * DEG, max_w);
+            o[k++] = touching(p, &rb[r], b, mg) ? 1.0 : 0.0;
+        }
+    }
+}
+
+/* actions [n][4] (dribbling) or [n][3] (pass endurance); obs [n][21] or [n][16];
+ * cmds_out [n][R][8] nullable */
+void orc_ssl_hw_env_step(orc_world *w, int task, const float *actions, int auto_reset, int max_steps,
+                         double *obs, double *reward, uint8_t *done, uint8_t *trunc, double *cmds_out) {
+    const rs_params *p = &w->p;
+    const int R = p->n_robots;
+    const int n_act = task == RS_TASK_SSL_DRIBBLING ? RS_DRIB_ACT : RS_PASS_ACT;
+    const int n_obs = task == RS_TASK_SSL_DRIBBLING ? RS_DRIB_OBS : RS_PASS_OBS;
+    const double max_v = 2.5, max_w = 10.0, max_kick_x = 5.0;
+    const double hl = p->length / 2, hw = p->width / 2;
+    const double ball_grad_scale = sqrt(hw * hw + hl * hl) / 4;       /* pass_endurance.py:68-70 */
+#pragma omp parallel for num_threads(w->n_threads) schedule(static)
+    for (int e = 0; e < w->n; ++e) {
+        o_ball *b = &w->ball[e]; o_robot *rb = &w->rob[(size_t)e * R];
+        double *info = w->info + (size_t)e * RS_SSL_INFO;
+        double cmd[RS_MAX_ROBOTS * RS_CMD_SSL];
+        double *mg = &w->margin[e]; *mg = 1e30;
+        memset(cmd, 0, sizeof(cmd));
+        if (w->steps[e] == 0) { memset(info, 0, sizeof(double) * RS_SSL_INFO); w->prev_pot[e] = 0.0; }
+        w->steps[e] += 1;
+        const float *a = actions + (size_t)e * n_act;
+        if (task == RS_TASK_SSL_DRIBBLING) {                           /* dribbling.py:107-133 */
+            double ang = rb[0].th;
+            double vx = a[0] * max_v, vy = a[1] * max_v, vth = a[2] * max_w;
+            double lx = vx * cos(ang) + vy * sin(ang), ly = -vx * sin(ang) + vy * cos(ang);
+            double vn = sqrt(lx * lx + ly * ly);
+            double c = vn < max_v ? 1.0 : max_v / vn;
+            cmd[1] = lx * c; cmd[2] = ly * c; cmd[3] = vth; cmd[7] = a[3] > 0 ? 1.0 : 0.0;
+        } else {                                                       /* pass_endurance.py:100-124 */
+            double a1 = fabsf(a[1]) > 0.5f ? a[1] : 0.0;
+            cmd[3] = a[0] * max_w; cmd[5] = a1 * max_kick_x; cmd[7] = a[2] > 0 ? 1.0 : 0.0;
+            cmd[RS_CMD_SSL + 7] = 1.0;                                 /* receiver: dribbler on, everything else 0 */
+        }
+        if (cmds_out) memcpy(cmds_out + (size_t)e * R * RS_CMD_SSL, cmd, sizeof(double) * R * RS_CMD_SSL);
+        const double lbx = b->x, lby = b->y;                           /* last_frame.ball */
+        step_env(p, b, rb, cmd, mg);
+        /* ssl_gym_base.py:83-85: the observation is taken BEFORE the reward updates the counter */
+        double *o = obs + (size_t)e * n_obs;
+        ssl_hw_obs(p, task, b, rb, w->prev_pot[e], o, mg);
+        double rew = 0.0; int dn = 0;
+        if (task == RS_TASK_SSL_DRIBBLING) {                           /* dribbling.py:135-185 */
+            const double n0 = -0.5, n1 = -1.0, n2 = -1.5, n3 = -2.0, fm = 1.0;
+            int cc = (int)w->prev_pot[e];
+            for (int r = p->n_blue; r < R; ++r) {
+                note(mg, fabs(rb[r].vx) - 0.05); note(mg, fabs(rb[r].vy) - 0.05);
+                if (fabs(rb[r].vx) > 0.05 || fabs(rb[r].vy) > 0.05) dn = 1;
+            }
+            note(mg, rb[0].x - (n3 - fm)); note(mg, rb[0].x - fm); note(mg, fabs(rb[0].y) - fm);
+            note(mg, b->y); note(mg, lby);
+            note(mg, b->x - n0); note(mg, b->x - n1); note(mg, b->x - n2); note(mg, b->x - n3); note(mg, b->x - (n3 - fm));
+            if (rb[0].x < n3 - fm || rb[0].x > fm || fabs(rb[0].y) > fm) dn = 1;
+            else if (cc == 0) {
+                if (b->x < n0 && b->x > n1 && lby >= 0 && b->y < 0) { rew = 1; cc += 1; }
+            } else if (cc == 1) {
+                if (b->x < n1 && b->x > n2 && lby < 0 && b->y >= 0) { rew = 1; cc += 1; }
+            } else if (cc % 2 == 0) {
+                if (b->x < n2 && b->x > n3) {
+                    if (lby >= 0 && b->y < 0) { rew = 1; cc += 1; if (cc == 7) dn = 1; }
+                    else if (lby < 0 && b->y >= 0) dn = 1;
+                }
+            } else {
+                if (b->x > n3 - fm && b->x < n3 && lby < 0 && b->y >= 0) { rew = 1; cc += 1; }
+            }
+            w->prev_pot[e] = (double)cc;
+        } else {                                                       /* pass_endurance.py:126-150, 183-233 */
+            const o_robot *sh = &rb[0], *rc = &rb[1];
+            const double ld = sqrt((lbx - rc->x) * (lbx - rc->x) + (lby - rc->y) * (lby - rc->y));
+            const double nd = sqrt((b->x - rc->x) * (b->x - rc->x) + (b->y - rc->y) * (b->y - rc->y));
+            if (touching(p, rc, b, mg)) { rew += 1; dn = 1; }
+            else {
+                const double g = clampd(ld - nd, -1, 1) / ball_grad_scale;
+                rew = g; info[1] += g;
+            }
+            /* __wrong_ball: centimetre-truncated box between shooter and receiver, 20-step stall counter */
+            const double cb[2] = {b->x * 100, b->y * 100}, cs[2] = {sh->x * 100, sh->y * 100}, cr[2] = {rc->x * 100, rc->y * 100};
+            int inside = 1;
+            for (int k = 0; k < 2; ++k) {
+                const int ib = (int)cb[k], is = (int)cs[k], ir = (int)cr[k];
+                note(mg, (cb[k] - floor(cb[k])) / 100); note(mg, (ceil(cb[k]) - cb[k]) / 100);
+                note(mg, (cs[k] - floor(cs[k])) / 100); note(mg, (ceil(cs[k]) - cs[k]) / 100);
+                note(mg, (cr[k] - floor(cr[k])) / 100); note(mg, (ceil(cr[k]) - cr[k]) / 100);
+                const int lo = is < ir ? is : ir, hi = is < ir ? ir : is;
+                if (!(lo <= ib && ib <= hi)) inside = 0;
+            }
+            note(mg, fabs(ld - nd) - 0.01);
+            int stopped_steps = (int)w->prev_pot[e];
+            stopped_steps = fabs(ld - nd) < 0.01 ? stopped_steps + 1 : 0;
+            w->prev_pot[e] = (double)stopped_steps;
+            if (stopped_steps > 20 || !inside) { rew -= 1; dn = 1; }
+            if (dn) {
+                const double dr = sqrt((rc->x - sh->x) * (rc->x - sh->x) + (rc->y - sh->y) * (rc->y - sh->y));
+                info[0] = (dr - nd) / dr;
+            }
+        }
+        reward[e] = rew; done[e] = (uint8_t)dn;
+        int tr = w->steps[e] >= max_steps;
+        trunc[e] = (uint8_t)tr;
+        if (auto_reset && (dn || tr)) {
+            place(w, task, e, RS_STREAM_AUTORESET); clear_task(w, e);
+            ssl_hw_obs(p, task, b, rb, 0.0, o, mg);
+        }
+    }
+    w->t++;
+}
+
 /* obs of the current frame without stepping (env.reset() return value) */
 void orc_task_obs(orc_world *w, int task, double *obs) {
     const rs_params *p = &w->p; const int R = p->n_robots;
     if (task == RS_TASK_VSS) {
         const int n_obs = 4 + 7 * p->n_blue + 5 * p->n_yellow;
         for (int e = 0; e < w->n; ++e) vss_obs(p, &w->ball[e], &w->rob[(size_t)e * R], obs + (size_t)e * n_obs);
+        return;
+    }
+    if (task == RS_TASK_SSL_DRIBBLING || task == RS_TASK_SSL_PASS_ENDURANCE) {
+        const int n_hw = task == RS_TASK_SSL_DRIBBLING ? RS_DRIB_OBS : RS_PASS_OBS;
+        for (int e = 0; e < w->n; ++e)
+            ssl_hw_obs(p, task, &w->ball[e], &w->rob[(size_t)e * R], w->steps[e] == 0 ? 0.0 : w->prev_pot[e],
+                       obs + (size_t)e * n_hw, NULL);
         return;
     }
     const int n_obs = 4 + 8 * p->n_blue + 2 * p->n_yellow;

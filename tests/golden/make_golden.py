@@ -163,6 +163,78 @@ def run_ssl(env_id, seed, steps, scripted):
     return out
 
 
+def run_ssl_hw(env_id, seed, steps, scripted):
+    """SSLDribbling-v0 / SSLPassEndurance-v0 (dribbling.py, pass_endurance.py): same record as
+    run_ssl plus the per-episode counter of the task before / after the step (dribbling:
+    checkpoints_count; pass endurance: stopped_steps) and pass endurance's reward_shaping_total."""
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env = gym.make(env_id)
+    u = env.unwrapped
+    drib = env_id == "SSLDribbling-v0"
+    R = u.n_robots_blue + u.n_robots_yellow
+    n_act = 4 if drib else 3
+    rec = {k: [] for k in ("raw_before", "steps_before", "counter_before", "action", "cmds", "obs", "reward",
+                           "done", "trunc", "state_after", "raw_after", "counter_after", "info_after")}
+    env.reset()
+
+    def counter():
+        return u.checkpoints_count if drib else u.stopped_steps
+
+    for t in range(steps):
+        a = rng.uniform(-1, 1, n_act).astype(np.float32)
+        if scripted and drib and t % 6 == 3:
+            # the ball about to cross y = 0 inside the x window of checkpoint cc (or just outside it),
+            # in the rewarded or in the reversed direction; the robot parked away from it
+            cc = int(rng.integers(0, 7))
+            lo, hi = {0: (-1.0, -0.5), 1: (-1.5, -1.0)}.get(cc, (-2.0, -1.5) if cc % 2 == 0 else (-3.0, -2.0))
+            raw = raw_of(env)
+            down = (cc % 2 == 0) != (rng.uniform() < 0.25)
+            raw[0] = rng.uniform(lo - 0.1, hi + 0.1); raw[1] = 0.004 if down else -0.004
+            raw[2] = 0.0; raw[3] = -2.0 if down else 2.0
+            raw[4] = raw[0] + 0.4; raw[5] = 0.5; raw[7:10] = 0.0
+            if rng.uniform() < 0.15:
+                raw[4] = 1.02                      # out of the course
+            set_raw(env, raw)
+            u.checkpoints_count = cc
+            a[:] = 0.0
+        if scripted and not drib and t % 8 == 4:
+            # the ball rolling into the receiver's mouth (infrared -> +1, done), or drifting out of the box
+            raw = raw_of(env)
+            rx, ry, rth = raw[10], raw[11], raw[12]
+            d = rng.uniform(0.13, 0.3)
+            off = rng.uniform(-0.02, 0.02) if rng.uniform() < 0.7 else rng.uniform(0.3, 0.6)
+            raw[0] = rx + d * np.cos(rth) - off * np.sin(rth); raw[1] = ry + d * np.sin(rth) + off * np.cos(rth)
+            raw[2] = -2.5 * np.cos(rth); raw[3] = -2.5 * np.sin(rth)
+            set_raw(env, raw)
+        if scripted and not drib and t % 8 != 4:
+            a[0] = rng.uniform(-0.2, 0.2); a[2] = 1.0
+            a[1] = 1.0 if t % 8 == 1 else rng.uniform(-0.6, 0.6)
+        rec["raw_before"].append(raw_of(env))
+        rec["steps_before"].append(u.steps)
+        rec["counter_before"].append(counter())
+        obs, rew, term, trunc, info = env.step(a.copy())        # pass_endurance.py:102 edits the action in place
+        rec["action"].append(a.astype(np.float64))
+        cm = np.zeros((R, 8))
+        for c in u.sent_commands:
+            row = (u.n_robots_blue + c.id) if c.yellow else c.id
+            cm[row] = (c.wheel_speed, c.v_x, c.v_y, c.v_theta, 0.0, c.kick_v_x, c.kick_v_z, c.dribbler)
+        rec["cmds"].append(cm.reshape(-1))
+        rec["obs"].append(obs.astype(np.float64))
+        rec["reward"].append(float(rew)); rec["done"].append(int(term)); rec["trunc"].append(int(trunc))
+        rec["state_after"].append(np.array(u.rsim.simulator.get_state()))
+        rec["raw_after"].append(raw_of(env))
+        rec["counter_after"].append(counter())
+        rst = getattr(u, "reward_shaping_total", None) or {}
+        rec["info_after"].append([float(rst.get("reversed_dist", 0.0)), float(rst.get("ball_grad", 0.0))])
+        if term or trunc:
+            env.reset()
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["field"] = np.array([getattr(u.field, k) for k in u.field.__dataclass_fields__])
+    return out
+
+
 def main():
     np.savez_compressed(os.path.join(HERE, "vss_v0_random.npz"), **run_vss(11, 260, False))
     np.savez_compressed(os.path.join(HERE, "vss_v0_goals.npz"), **run_vss(12, 200, True))
@@ -174,6 +246,12 @@ def main():
                         **run_ssl("SSLContestedPossession-v0", 31, 200, False))
     np.savez_compressed(os.path.join(HERE, "ssl_contested_possession_fetch.npz"),
                         **run_ssl("SSLContestedPossession-v0", 32, 240, True))
+    np.savez_compressed(os.path.join(HERE, "ssl_dribbling_random.npz"), **run_ssl_hw("SSLDribbling-v0", 41, 200, False))
+    np.savez_compressed(os.path.join(HERE, "ssl_dribbling_course.npz"), **run_ssl_hw("SSLDribbling-v0", 42, 300, True))
+    np.savez_compressed(os.path.join(HERE, "ssl_pass_endurance_random.npz"),
+                        **run_ssl_hw("SSLPassEndurance-v0", 51, 200, False))
+    np.savez_compressed(os.path.join(HERE, "ssl_pass_endurance_catch.npz"),
+                        **run_ssl_hw("SSLPassEndurance-v0", 52, 300, True))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             d = np.load(os.path.join(HERE, f))

@@ -14,6 +14,9 @@ G = os.path.join(HERE, "golden")
 VSS_FILES = ["vss_v0_random.npz", "vss_v0_goals.npz"]
 SSL_FILES = [("ssl_static_defenders_random.npz", 1, 1, 6, 1000), ("ssl_static_defenders_fetch.npz", 1, 1, 6, 1000),
              ("ssl_contested_possession_random.npz", 2, 1, 1, 1200), ("ssl_contested_possession_fetch.npz", 2, 1, 1, 1200)]
+# SSLDribbling-v0 (task 3: 1 blue + 4 yellow) and SSLPassEndurance-v0 (task 4: 2 blue)
+HW_FILES = [("ssl_dribbling_random.npz", 3, 1, 4, 4800), ("ssl_dribbling_course.npz", 3, 1, 4, 4800),
+            ("ssl_pass_endurance_random.npz", 4, 2, 0, 1200), ("ssl_pass_endurance_catch.npz", 4, 2, 0, 1200)]
 
 
 def _load(name):
@@ -67,6 +70,34 @@ def test_oracle_ssl_env_step_vs_reference(oracle, name, task, nb, ny, max_steps)
     assert np.abs(rew - d["reward"]).max() < 1e-6
     if "fetch" in name:
         assert d["done"].sum() >= 3 and (d["obs"][:, 11] > 0.5).sum() > 5     # infrared seen
+
+
+@pytest.mark.parametrize("name,task,nb,ny,max_steps", HW_FILES)
+def test_oracle_ssl_hw_env_step_vs_reference(oracle, name, task, nb, ny, max_steps):
+    """dribbling.py / pass_endurance.py: commands, observation (taken before the reward updates
+    the checkpoint counter, ssl_gym_base.py:83-85), reward, done and the task counter."""
+    d = _load(name)
+    T = len(d["reward"])
+    w = oracle.OracleWorld(1, 2, nb, ny, 25, T)
+    w.set_raw(d["raw_before"])
+    w.set_task_state(steps=np.maximum(d["steps_before"], 1), prev_pot=d["counter_before"].astype(np.float64),
+                     info=np.zeros((T, 9)))
+    obs, rew, done, trunc, cmds = w.ssl_env_step(task, d["action"].astype(np.float32), auto_reset=False,
+                                                 max_steps=max_steps, want_cmds=True)
+    assert np.abs(cmds.reshape(T, -1) - d["cmds"]).max() < 1e-6
+    assert (done == d["done"]).all()
+    assert np.abs(w.get_state() - d["state_after"]).max() < 1e-4
+    assert np.abs(obs - d["obs"]).max() < 2e-6
+    assert np.abs(rew - d["reward"]).max() < 1e-6
+    ts = w.get_task_state()
+    assert (ts["prev_pot"] == d["counter_after"]).all()
+    if task == 4:
+        dn = d["done"] == 1
+        assert np.abs(ts["info"][dn, 0] - d["info_after"][dn, 0]).max() < 1e-9       # reversed_dist
+    if "course" in name:
+        assert d["reward"].sum() >= 10 and d["done"].sum() >= 5 and len(set(d["counter_after"])) >= 6
+    if "catch" in name:
+        assert (d["reward"] > 0.9).sum() >= 5 and (d["reward"] < -0.5).sum() >= 5
 
 
 @pytest.mark.gpu

@@ -108,8 +108,9 @@ def main():
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=300, help="untimed steps per world")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--graph-steps", type=int, default=0, help="steps per captured graph (default: one pass over the worlds)")
     a = ap.parse_args()
-    us = time_steps(a.task, a.envs, a.worlds, a.steps, a.warmup, not a.no_graph)
+    us = time_steps(a.task, a.envs, a.worlds, a.steps, a.warmup, not a.no_graph, a.graph_steps)
     mode = "per_match" if os.environ.get("RS_PER_MATCH", "") == "1" else ("per_body" if os.environ.get("RS_PER_MATCH", "") == "0" else "auto")
     print("TIMING task=%s envs=%d mode=%s pdl=%s graph=%d  %.2f us/step  %.1f Menv-steps/s" % (
         a.task, a.envs, mode, os.environ.get("RS_PDL", "1"), not a.no_graph, us, a.envs / us))
