@@ -126,9 +126,13 @@ int rs_sync_t(rs_world *w, void *stream);
 #define RS_TASK_VSS_V0 0
 #define RS_TASK_SSL_STATIC_DEFENDERS_V0 1
 #define RS_TASK_SSL_CONTESTED_POSSESSION_V0 2
+#define RS_TASK_SSL_DRIBBLING_V0 3          /* world: SSL, field_type 2, 1 blue + 4 yellow (dribbling.py:47-49) */
+#define RS_TASK_SSL_PASS_ENDURANCE_V0 4     /* world: SSL, field_type 2, 2 blue (pass_endurance.py:46-52) */
 
-/* observation width of a task for this world (40 / 24 / 14 at the reference sizes) */
+/* observation width of a task for this world (40 / 24 / 14 / 21 / 16 at the reference sizes) */
 int rs_task_obs_dim(const rs_world *w, int task);
+/* action width of a task: 2 / 5 / 5 / 4 / 3 */
+int rs_task_act_dim(int task);
 
 /* env.reset() for the envs selected by d_mask (nullable = all): random initial
  * frame per the task's _get_initial_positions_frame, drawn on device; writes the
@@ -145,7 +149,9 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
                     int max_steps, float *d_obs, float *d_reward, uint8_t *d_done,
                     uint8_t *d_trunc, float *d_cmds_out, void *stream);
 
-/* SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step; d_actions [N][5] */
+/* SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step (d_actions [N][5]),
+ * SSLHWDribblingEnv.step (d_actions [N][4], obs [N][21]) and SSLPassEnduranceEnv.step
+ * (d_actions [N][3], obs [N][16]); rows are rs_task_act_dim / rs_task_obs_dim wide */
 int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_reset, int max_steps,
                     float *d_obs, float *d_reward, uint8_t *d_done, uint8_t *d_trunc,
                     float *d_cmds_out, void *stream);

@@ -924,8 +924,14 @@ void orc_ssl_hw_env_step(orc_world *w, int task, const float *actions, int auto_
                 if (fabs(rb[r].vx) > 0.05 || fabs(rb[r].vy) > 0.05) dn = 1;
             }
             note(mg, rb[0].x - (n3 - fm)); note(mg, rb[0].x - fm); note(mg, fabs(rb[0].y) - fm);
-            note(mg, b->y); note(mg, lby);
-            note(mg, b->x - n0); note(mg, b->x - n1); note(mg, b->x - n2); note(mg, b->x - n3); note(mg, b->x - (n3 - fm));
+            {   /* margins of the checkpoint test: the x window of this counter value matters only if
+                 * the ball crossed y = 0, the sign of the new y only inside the window (the old y is
+                 * an input, identical in every precision) */
+                const double wlo = cc == 0 ? n1 : cc == 1 ? n2 : (cc % 2 == 0 ? n3 : n3 - fm);
+                const double whi = cc == 0 ? n0 : cc == 1 ? n1 : (cc % 2 == 0 ? n2 : n3);
+                if ((lby >= 0) != (b->y >= 0)) { note(mg, b->x - wlo); note(mg, b->x - whi); }
+                if (b->x < whi && b->x > wlo) note(mg, b->y);
+            }
             if (rb[0].x < n3 - fm || rb[0].x > fm || fabs(rb[0].y) > fm) dn = 1;
             else if (cc == 0) {
                 if (b->x < n0 && b->x > n1 && lby >= 0 && b->y < 0) { rew = 1; cc += 1; }

@@ -26,12 +26,13 @@ NVCC_FLAGS = [
 RS_OK = 0
 ARR_BODY, ARR_ANG, ARR_OU, ARR_PREV, ARR_STEPS, ARR_INFO, ARR_COUNT = 0, 1, 2, 3, 4, 5, 6
 TASK_VSS_V0, TASK_SSL_STATIC_DEFENDERS_V0, TASK_SSL_CONTESTED_POSSESSION_V0 = 0, 1, 2
+TASK_SSL_DRIBBLING_V0, TASK_SSL_PASS_ENDURANCE_V0 = 3, 4
 
 # every symbol include/rsoccer_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_state_bytes", "rs_bind_state",
     "rs_layout", "rs_field_params", "rs_reset", "rs_step", "rs_get_state", "rs_set_raw",
-    "rs_get_raw", "rs_get_t", "rs_set_t", "rs_sync_t", "rs_task_obs_dim", "rs_task_reset", "rs_vss_env_step",
+    "rs_get_raw", "rs_get_t", "rs_set_t", "rs_sync_t", "rs_task_obs_dim", "rs_task_act_dim", "rs_task_reset", "rs_vss_env_step",
     "rs_ssl_env_step", "rs_vss_env_step_host", "rs_ssl_env_step_host", "rs_launch_count", "rs_kernel_flags",
 )
 
@@ -99,6 +100,8 @@ def lib():
     L.rs_ssl_env_step.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.rs_vss_env_step_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.rs_ssl_env_step_host.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.rs_task_act_dim.restype = i32
+    L.rs_task_act_dim.argtypes = [i32]
     L.rs_launch_count.restype = u64
     L.rs_launch_count.argtypes = [vp]
     L.rs_kernel_flags.restype = i32

@@ -474,6 +474,143 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
     warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS);
 }
 
+// SSLHWDribblingEnv.step (TASK 3: 1 blue + 4 yellow, dribbling.py) and SSLPassEnduranceEnv.step
+// (TASK 4: 2 blue, pass_endurance.py), one lane per match.  The per-episode counter of the
+// task (dribbling: checkpoints_count; pass endurance: stopped_steps) lives in the `prev` word;
+// info[0..1] of pass endurance = reward_shaping_total {reversed_dist, ball_grad}
+// (pass_endurance.py:113-114).  pass_endurance.py never increments holding_steps (:56, :92,
+// :121), so its `> 15` test never fires and is not restated.
+template <int TASK, int NB, int NY, int BS>
+__global__ void __launch_bounds__(BS)
+k_ssl_hw_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
+    constexpr int R = NB + NY;
+    constexpr bool DRIB = TASK == RS_TASK_SSL_DRIBBLING;
+    constexpr int NACT = DRIB ? RS_DRIB_ACT : RS_PASS_ACT, NOBS = DRIB ? RS_DRIB_OBS : RS_PASS_OBS;
+    const int e = blockIdx.x * BS + threadIdx.x;
+    const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
+    pdl_wait();
+    pdl_release();
+    if (e >= S.n) return;
+    Scene<R> s;
+    load_scene<R>(P, S, e, s);
+    int steps = S.steps[e] & 0xFFFFFF;
+    float counter = steps == 0 ? 0.0f : S.prev[e];
+    float info0 = steps == 0 ? 0.0f : S.info[e], info1 = steps == 0 ? 0.0f : S.info[(size_t)S.np + e];
+    steps += 1;
+    const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
+    float a[NACT];
+#pragma unroll
+    for (int i = 0; i < NACT; ++i) a[i] = A.actions[(size_t)e * NACT + i];
+    const float max_v = 2.5f, max_w = 10.0f, max_kick_x = 5.0f;
+    float cmd[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cmd[r][i] = 0.0f;
+    if (DRIB) {                                   // dribbling.py:107-133
+        float sn, cs;
+        __sincosf(s.th[0], &sn, &cs);
+        const float vx = a[0] * max_v, vy = a[1] * max_v;
+        const float lx = vx * cs + vy * sn, ly = -vx * sn + vy * cs;
+        const float vn2 = lx * lx + ly * ly;
+        const float c = vn2 < max_v * max_v ? 1.0f : max_v * rsqrtf(vn2);
+        cmd[0][1] = lx * c; cmd[0][2] = ly * c; cmd[0][3] = a[2] * max_w; cmd[0][7] = a[NACT - 1] > 0.0f ? 1.0f : 0.0f;
+    } else {                                      // pass_endurance.py:100-124
+        const float a1 = fabsf(a[1]) > 0.5f ? a[1] : 0.0f;
+        cmd[0][3] = a[0] * max_w; cmd[0][5] = a1 * max_kick_x; cmd[0][7] = a[2] > 0.0f ? 1.0f : 0.0f;
+        cmd[R > 1 ? 1 : 0][7] = 1.0f;             // the receiver: dribbler on, everything else 0
+    }
+    Drive<R> d;
+    d.drib = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (r < NB) {
+            bool drib;
+            ssl_target(P, cmd[r], d.tf[r], d.tl[r], d.tw[r], d.kick[r], drib);
+            if (drib) d.drib |= 1u << r;
+        } else { d.tf[r] = 0.0f; d.tl[r] = 0.0f; d.tw[r] = 0.0f; d.kick[r] = 0.0f; }
+    }
+    if (A.cmds_out) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) A.cmds_out[((size_t)e * R + r) * 8 + i] = cmd[r][i];
+    }
+    const float lbx = s.bx, lby = s.by;           // last_frame.ball
+
+    physics_step<RS_KIND_SSL, R>(P, s, d, live);
+
+    // ssl_gym_base.py:83-85: the observation is taken BEFORE the reward updates the counter
+    float *o = A.obs + (size_t)e * NOBS;
+    ssl_hw_obs<TASK>(P, s, counter, o);
+    float rew = 0.0f; bool dn = false;
+    if (DRIB) {                                   // dribbling.py:135-185
+        const float n0 = -0.5f, n1 = -1.0f, n2 = -1.5f, n3 = -2.0f, fm = 1.0f;
+        int cc = (int)counter;
+#pragma unroll
+        for (int r = NB; r < R; ++r) if (fabsf(s.vx[r]) > 0.05f || fabsf(s.vy[r]) > 0.05f) dn = true;
+        if (s.x[0] < n3 - fm || s.x[0] > fm || fabsf(s.y[0]) > fm) dn = true;
+        else if (cc == 0) {
+            if (s.bx < n0 && s.bx > n1 && lby >= 0.0f && s.by < 0.0f) { rew = 1.0f; cc += 1; }
+        } else if (cc == 1) {
+            if (s.bx < n1 && s.bx > n2 && lby < 0.0f && s.by >= 0.0f) { rew = 1.0f; cc += 1; }
+        } else if (cc % 2 == 0) {
+            if (s.bx < n2 && s.bx > n3) {
+                if (lby >= 0.0f && s.by < 0.0f) { rew = 1.0f; cc += 1; if (cc == 7) dn = true; }
+                else if (lby < 0.0f && s.by >= 0.0f) dn = true;
+            }
+        } else {
+            if (s.bx > n3 - fm && s.bx < n3 && lby < 0.0f && s.by >= 0.0f) { rew = 1.0f; cc += 1; }
+        }
+        counter = (float)cc;
+    } else {                                      // pass_endurance.py:126-150, 183-233
+        constexpr int RC = R > 1 ? 1 : 0;
+        const float ball_grad_scale = sqrtf(P.half_wid * P.half_wid + P.half_len * P.half_len) * 0.25f;
+        const float ld = sqrtf((lbx - s.x[RC]) * (lbx - s.x[RC]) + (lby - s.y[RC]) * (lby - s.y[RC]));
+        const float nd = sqrtf((s.bx - s.x[RC]) * (s.bx - s.x[RC]) + (s.by - s.y[RC]) * (s.by - s.y[RC]));
+        float sn, cs;
+        __sincosf(s.th[RC], &sn, &cs);
+        if (touching(P, s.x[RC], s.y[RC], cs, sn, s.bx, s.by)) { rew += 1.0f; dn = true; }
+        else {
+            const float g = clampf(ld - nd, -1.0f, 1.0f) / ball_grad_scale;
+            rew = g; info1 += g;
+        }
+        // __wrong_ball: centimetre-truncated box between shooter and receiver, 20-step stall counter
+        const int ibx = (int)(s.bx * 100.0f), iby = (int)(s.by * 100.0f);
+        const int isx = (int)(s.x[0] * 100.0f), isy = (int)(s.y[0] * 100.0f);
+        const int irx = (int)(s.x[RC] * 100.0f), iry = (int)(s.y[RC] * 100.0f);
+        const bool inside = min(isx, irx) <= ibx && ibx <= max(isx, irx) && min(isy, iry) <= iby && iby <= max(isy, iry);
+        int stopped = (int)counter;
+        stopped = fabsf(ld - nd) < 0.01f ? stopped + 1 : 0;
+        counter = (float)stopped;
+        if (stopped > 20 || !inside) { rew -= 1.0f; dn = true; }
+        if (dn) {
+            const float dr = sqrtf((s.x[RC] - s.x[0]) * (s.x[RC] - s.x[0]) + (s.y[RC] - s.y[0]) * (s.y[RC] - s.y[0]));
+            info0 = (dr - nd) / dr;
+        }
+    }
+    const bool tr = steps >= A.max_steps;
+    A.reward[e] = rew; A.done[e] = dn ? 1 : 0; A.trunc[e] = tr ? 1 : 0;
+    S.info[e] = info0; S.info[(size_t)S.np + e] = info1;
+    if (A.auto_reset && (dn || tr)) {
+        Scene<0> tmp;
+        task_place<TASK, 0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, t_now, RS_STREAM_AUTORESET), tmp);
+        s.bx = tmp.bx; s.by = tmp.by; s.bvx = 0.0f; s.bvy = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            s.x[r] = tmp.x[r]; s.y[r] = tmp.y[r]; s.th[r] = tmp.th[r];
+            s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+        }
+        steps = 0; counter = 0.0f;
+        ssl_hw_obs<TASK>(P, s, 0.0f, o);
+    }
+    store_scene<R>(P, S, e, s);
+    S.steps[e] = steps;
+    S.prev[e] = counter;
+    step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
+}
+
+
 // SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step, one lane per BODY
 // (rs_lanes.cuh): L lanes per match (8 for 1 v 6, 4 for 1 v 1).  Lane b owns task words
 // b, b + L, ... of the 2 + RS_SSL_INFO words of its match.
@@ -813,6 +950,8 @@ __global__ void k_task_reset(const DevParams P, const StatePtrs S, const uint8_t
             o[k++] = nrm(s.vx[r], P.inv_max_v); o[k++] = nrm(s.vy[r], P.inv_max_v);
             o[k++] = nrm(s.om[r], P.inv_max_w_rad);
         }
+    } else if (TASK == RS_TASK_SSL_DRIBBLING || TASK == RS_TASK_SSL_PASS_ENDURANCE) {
+        ssl_hw_obs<TASK>(P, s, 0.0f, o);
     } else {
         const float inv_v = 1.0f / 2.5f, inv_w = RS_DEG_F / 10.0f;
         o[k++] = nrm(s.bx, P.inv_max_pos); o[k++] = nrm(s.by, P.inv_max_pos);
@@ -1182,6 +1321,8 @@ static bool task_matches(const rs_world *w, int task) {
     if (task == RS_TASK_VSS_V0) return p.kind == RS_KIND_VSS && p.n_blue == 3 && p.n_yellow == 3;
     if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) return p.kind == RS_KIND_SSL && p.n_blue == 1 && p.n_yellow == 6;
     if (task == RS_TASK_SSL_CONTESTED_POSSESSION_V0) return p.kind == RS_KIND_SSL && p.n_blue == 1 && p.n_yellow == 1;
+    if (task == RS_TASK_SSL_DRIBBLING_V0) return p.kind == RS_KIND_SSL && p.n_blue == 1 && p.n_yellow == 4;
+    if (task == RS_TASK_SSL_PASS_ENDURANCE_V0) return p.kind == RS_KIND_SSL && p.n_blue == 2 && p.n_yellow == 0;
     return false;
 }
 
@@ -1190,7 +1331,19 @@ int rs_task_obs_dim(const rs_world *w, int task) {
     if (task == RS_TASK_VSS_V0) return 4 + 7 * w->p.n_blue + 5 * w->p.n_yellow;
     if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0 || task == RS_TASK_SSL_CONTESTED_POSSESSION_V0)
         return 4 + 8 * w->p.n_blue + 2 * w->p.n_yellow;
+    if (task == RS_TASK_SSL_DRIBBLING_V0) return 5 + 8 * w->p.n_blue + 2 * w->p.n_yellow;     // dribbling.py:53
+    if (task == RS_TASK_SSL_PASS_ENDURANCE_V0) return 4 + 6 * w->p.n_blue;                     // pass_endurance.py:55
     return fail(RS_E_INVALID, "rs_task_obs_dim: unknown task");
+}
+
+int rs_task_act_dim(int task) {
+    switch (task) {
+        case RS_TASK_VSS_V0: return RS_VSS_ACT;
+        case RS_TASK_SSL_STATIC_DEFENDERS_V0: case RS_TASK_SSL_CONTESTED_POSSESSION_V0: return RS_SSL_ACT;
+        case RS_TASK_SSL_DRIBBLING_V0: return RS_DRIB_ACT;
+        case RS_TASK_SSL_PASS_ENDURANCE_V0: return RS_PASS_ACT;
+        default: return fail(RS_E_INVALID, "rs_task_act_dim: unknown task");
+    }
 }
 
 int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, void *stream) {
@@ -1203,6 +1356,8 @@ int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, vo
     const uint32_t *t = w->d_ctr;
     if (task == RS_TASK_VSS_V0) k_task_reset<RS_TASK_VSS><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
     else if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) k_task_reset<RS_TASK_SSL_STATIC_DEFENDERS><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
+    else if (task == RS_TASK_SSL_DRIBBLING_V0) k_task_reset<RS_TASK_SSL_DRIBBLING><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
+    else if (task == RS_TASK_SSL_PASS_ENDURANCE_V0) k_task_reset<RS_TASK_SSL_PASS_ENDURANCE><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
     else k_task_reset<RS_TASK_SSL_CONTESTED_POSSESSION><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
     w->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1251,7 +1406,7 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
                     float *d_obs, float *d_reward, uint8_t *d_done, uint8_t *d_trunc,
                     float *d_cmds_out, void *stream) {
     NEED_STATE(w, "rs_ssl_env_step");
-    if ((task != RS_TASK_SSL_STATIC_DEFENDERS_V0 && task != RS_TASK_SSL_CONTESTED_POSSESSION_V0) || !task_matches(w, task))
+    if (task < RS_TASK_SSL_STATIC_DEFENDERS_V0 || task > RS_TASK_SSL_PASS_ENDURANCE_V0 || !task_matches(w, task))
         return fail(RS_E_UNSUPPORTED, "rs_ssl_env_step: task does not match this world");
     if (!d_actions || !d_obs || !d_reward || !d_done || !d_trunc)
         return fail(RS_E_INVALID, "rs_ssl_env_step: null argument");
@@ -1264,7 +1419,11 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
-    if (use_lane_per_body(w, true)) {
+    if (task == RS_TASK_SSL_DRIBBLING_V0) {
+        launch_step_kernel(k_ssl_hw_env_step<RS_TASK_SSL_DRIBBLING, 1, 4, 64>, g64, 64, st, w->dp, S, A);
+    } else if (task == RS_TASK_SSL_PASS_ENDURANCE_V0) {
+        launch_step_kernel(k_ssl_hw_env_step<RS_TASK_SSL_PASS_ENDURANCE, 2, 0, 64>, g64, 64, st, w->dp, S, A);
+    } else if (use_lane_per_body(w, true)) {
         // lane per body: 8 lanes per 1 v 6 match, 4 per 1 v 1 match
         const int bs = w->lane_block;
         if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
@@ -1346,10 +1505,12 @@ int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto
         return fail(RS_E_INVALID, "rs_ssl_env_step_host: null argument");
     const int od = rs_task_obs_dim(w, task);
     if (od < 0) return od;
-    int rc = ensure_scratch(w, RS_SSL_ACT, od);
+    const int ad = rs_task_act_dim(task);
+    if (ad < 0) return ad;
+    int rc = ensure_scratch(w, ad, od);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemcpyAsync(w->s_actions, h_actions, sizeof(float) * (size_t)w->n * RS_SSL_ACT, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(w->s_actions, h_actions, sizeof(float) * (size_t)w->n * ad, cudaMemcpyHostToDevice, st));
     rc = rs_ssl_env_step(w, task, w->s_actions, auto_reset, max_steps, w->s_obs, w->s_reward, w->s_done, w->s_trunc, nullptr, stream);
     if (rc) return rc;
     return host_epilogue(w, od, h_obs, h_reward, h_done, h_trunc, st);

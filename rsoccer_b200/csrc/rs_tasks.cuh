@@ -183,9 +183,63 @@ __device__ __noinline__ void ssl_cp_place(const DevParams &P, Rng g, Scene<RT> &
         s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
     }
 }
+// dribbling.py:187-202: fixed course, the robot at the origin facing -x with the ball in its mouth
+template <int RT>
+__device__ __noinline__ void ssl_drib_place(const DevParams &P, Rng g, Scene<RT> &s) {
+    const int R = RT > 0 ? RT : P.n_robots;
+    s.bx = -0.1f; s.by = 0.0f; s.bvx = 0.0f; s.bvy = 0.0f;
+    for (int r = 0; r < R; ++r) {
+        s.x[r] = r == 0 ? 0.0f : -0.5f * (float)r; s.y[r] = 0.0f; s.th[r] = RS_PI_F;
+        s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+    }
+}
+// pass_endurance.py:152-181: ball anywhere in [-1.5, 1.5]^2, the shooter 0.115 m behind it facing it
+// along y, the receiver mirrored in y and at least 1 m away in x, facing the shooter
+template <int RT>
+__device__ __noinline__ void ssl_pass_place(const DevParams &P, Rng g, Scene<RT> &s) {
+    s.bx = g.uniform(-1.5f, 1.5f); s.by = g.uniform(1.5f, -1.5f); s.bvx = 0.0f; s.bvy = 0.0f;
+    const float factor = s.by < 0.0f ? -1.0f : 1.0f;
+    s.x[0] = s.bx; s.y[0] = s.by + 0.115f * factor; s.th[0] = factor > 0.0f ? -0.5f * RS_PI_F : 0.5f * RS_PI_F;
+    float rx = 0.0f;
+    for (int tries = 0; tries < 64; ++tries) {
+        rx = g.uniform(-1.5f, 1.5f);
+        if (!(fabsf(rx - s.bx) < 1.0f)) break;
+    }
+    s.x[1] = rx; s.y[1] = -s.by;
+    s.th[1] = wrap_pi(atan2f(s.y[1] - s.y[0], s.x[1] - s.x[0]) + RS_PI_F);
+    for (int r = 0; r < 2; ++r) { s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f; }
+}
 template <int TASK, int RT>
 __device__ __forceinline__ void task_place(const DevParams &P, const Rng &g, Scene<RT> &s) {
     if (TASK == RS_TASK_VSS) vss_place<RT>(P, g, s);
     else if (TASK == RS_TASK_SSL_STATIC_DEFENDERS) ssl_sd_place<RT>(P, g, s);
+    else if (TASK == RS_TASK_SSL_DRIBBLING) ssl_drib_place<RT>(P, g, s);
+    else if (TASK == RS_TASK_SSL_PASS_ENDURANCE) ssl_pass_place<RT>(P, g, s);
     else ssl_cp_place<RT>(P, g, s);
+}
+
+// dribbling.py:75-105 (21 floats: checkpoint progress first, infrared as +-1) and
+// pass_endurance.py:78-90 (16 floats: no robot velocities, infrared as 1 / 0); the scene type is
+// generic so that k_task_reset (Scene<0>) shares it
+template <int TASK, class SC>
+__device__ __forceinline__ void ssl_hw_obs(const DevParams &P, const SC &s, const float counter, float *o) {
+    const float inv_v = 1.0f / 2.5f, inv_w = RS_DEG_F / 10.0f;     // dribbling.py:66-67, pass_endurance.py:73-74
+    const int NB = TASK == RS_TASK_SSL_DRIBBLING ? 1 : 2, R = TASK == RS_TASK_SSL_DRIBBLING ? 5 : 2;
+    int k = 0;
+    if (TASK == RS_TASK_SSL_DRIBBLING) o[k++] = ((counter / 6.0f) * 2.0f) - 1.0f;
+    o[k++] = nrm(s.bx, P.inv_max_pos); o[k++] = nrm(s.by, P.inv_max_pos);
+    o[k++] = nrm(s.bvx, inv_v); o[k++] = nrm(s.bvy, inv_v);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+        float sn, cs;
+        __sincosf(s.th[r], &sn, &cs);
+        o[k++] = nrm(s.x[r], P.inv_max_pos); o[k++] = nrm(s.y[r], P.inv_max_pos);
+        o[k++] = sn; o[k++] = cs;
+        if (TASK == RS_TASK_SSL_DRIBBLING) { o[k++] = nrm(s.vx[r], inv_v); o[k++] = nrm(s.vy[r], inv_v); }
+        o[k++] = nrm(s.om[r], inv_w);
+        const bool ir = touching(P, s.x[r], s.y[r], cs, sn, s.bx, s.by);
+        o[k++] = ir ? 1.0f : (TASK == RS_TASK_SSL_DRIBBLING ? -1.0f : 0.0f);
+    }
+#pragma unroll
+    for (int r = NB; r < R; ++r) { o[k++] = nrm(s.x[r], P.inv_max_pos); o[k++] = nrm(s.y[r], P.inv_max_pos); }
 }

@@ -15,6 +15,8 @@ KIND_VSS, KIND_SSL = 0, 1
 TASK_VSS_V0 = _lib.TASK_VSS_V0
 TASK_SSL_STATIC_DEFENDERS_V0 = _lib.TASK_SSL_STATIC_DEFENDERS_V0
 TASK_SSL_CONTESTED_POSSESSION_V0 = _lib.TASK_SSL_CONTESTED_POSSESSION_V0
+TASK_SSL_DRIBBLING_V0 = _lib.TASK_SSL_DRIBBLING_V0
+TASK_SSL_PASS_ENDURANCE_V0 = _lib.TASK_SSL_PASS_ENDURANCE_V0
 
 FIELD_KEYS = (
     "length", "width", "penalty_length", "penalty_width", "goal_width", "goal_depth",
@@ -189,7 +191,8 @@ class BatchedWorld:
         return obs, rew, done, trunc
 
     def ssl_env_step(self, task, actions, auto_reset=True, max_steps=1000, out=None, cmds_out=None):
-        a = self._f32(actions, (self.n, 5))
+        """static defenders / contested possession (5 actions), dribbling (4), pass endurance (3)"""
+        a = self._f32(actions, (self.n, int(self.L.rs_task_act_dim(task))))
         obs, rew, done, trunc = out if out is not None else self.alloc_outputs(task)
         _lib.check(self.L.rs_ssl_env_step(self.h, task, _ptr(a), int(auto_reset), int(max_steps),
                                           _ptr(obs), _ptr(rew), _ptr(done), _ptr(trunc),

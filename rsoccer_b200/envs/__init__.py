@@ -1,12 +1,15 @@
-"""Batched envs.  `make(id, num_envs=...)` mirrors gym.make for the ids the reference
-registers (rsoccer_gym/__init__.py:3-30) that are in scope (BASELINE.json configs)."""
+"""Batched envs.  `make(id, num_envs=...)` mirrors gym.make for the five ids the reference
+registers (rsoccer_gym/__init__.py:3-30)."""
 from .base import BoxSpec, SSLBaseVecEnv, VSSBaseVecEnv
-from .fused import SSLContestedPossessionVecEnv, SSLStaticDefendersVecEnv, VSSVecEnv
+from .fused import (SSLContestedPossessionVecEnv, SSLDribblingVecEnv, SSLPassEnduranceVecEnv,
+                    SSLStaticDefendersVecEnv, VSSVecEnv)
 
 REGISTRY = {
     "VSS-v0": VSSVecEnv,
     "SSLStaticDefenders-v0": SSLStaticDefendersVecEnv,
     "SSLContestedPossession-v0": SSLContestedPossessionVecEnv,
+    "SSLDribbling-v0": SSLDribblingVecEnv,
+    "SSLPassEndurance-v0": SSLPassEnduranceVecEnv,
 }
 
 
@@ -17,4 +20,5 @@ def make(id, num_envs=1, **kwargs):
 
 
 __all__ = ["make", "REGISTRY", "BoxSpec", "VSSBaseVecEnv", "SSLBaseVecEnv", "VSSVecEnv",
-           "SSLStaticDefendersVecEnv", "SSLContestedPossessionVecEnv"]
+           "SSLStaticDefendersVecEnv", "SSLContestedPossessionVecEnv", "SSLDribblingVecEnv",
+           "SSLPassEnduranceVecEnv"]

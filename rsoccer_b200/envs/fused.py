@@ -1,8 +1,10 @@
-"""The three benchmarked reference envs as batched envs whose `step` is ONE fused launch.
+"""The five registered reference envs as batched envs whose `step` is ONE fused launch.
 
     VSSVecEnv                       <- rsoccer_gym/vss/env_vss/vss_gym.py           (VSS-v0)
     SSLStaticDefendersVecEnv        <- ssl/ssl_hw_challenge/static_defenders.py     (SSLStaticDefenders-v0)
     SSLContestedPossessionVecEnv    <- ssl/ssl_hw_challenge/contested_possession.py (SSLContestedPossession-v0)
+    SSLDribblingVecEnv              <- ssl/ssl_hw_challenge/dribbling.py            (SSLDribbling-v0)
+    SSLPassEnduranceVecEnv          <- ssl/ssl_hw_challenge/pass_endurance.py       (SSLPassEndurance-v0)
 
 API (gymnasium VectorEnv flavour, same-step auto-reset):
     obs, info = env.reset()
@@ -126,3 +128,23 @@ class SSLStaticDefendersVecEnv(_SSLFused):
 class SSLContestedPossessionVecEnv(_SSLFused):
     TASK, N_BLUE, N_YELLOW = _E.TASK_SSL_CONTESTED_POSSESSION_V0, 1, 1
     MAX_EPISODE_STEPS = 1200              # rsoccer_gym/__init__.py:24
+
+
+class SSLDribblingVecEnv(_SSLFused):
+    """SSLDribbling-v0: zig-zag course between four parked robots; `checkpoints` (the reference's
+    checkpoints_count, dribbling.py:56) is a zero-copy [N] view of the on-device counter."""
+    TASK, N_BLUE, N_YELLOW, ACT_DIM = _E.TASK_SSL_DRIBBLING_V0, 1, 4, 4
+    MAX_EPISODE_STEPS = 4800              # rsoccer_gym/__init__.py:17
+    INFO_KEYS = ()                        # ssl_gym_base.py:88 returns {} and dribbling.py adds nothing
+
+    @property
+    def checkpoints(self):
+        return self.world.prev_pot[:self.num_envs]
+
+
+class SSLPassEnduranceVecEnv(_SSLFused):
+    """SSLPassEndurance-v0: the shooter turns / kicks, the receiver holds its dribbler on;
+    info = reward_shaping_total {reversed_dist, ball_grad} (pass_endurance.py:113-114)."""
+    TASK, N_BLUE, N_YELLOW, ACT_DIM = _E.TASK_SSL_PASS_ENDURANCE_V0, 2, 0, 3
+    MAX_EPISODE_STEPS = 1200              # rsoccer_gym/__init__.py:29
+    INFO_KEYS = ("reversed_dist", "ball_grad")

@@ -148,3 +148,30 @@ def test_cuda_ssl_env_step_vs_reference(engine, name, task, nb, ny, max_steps):
     er = np.abs(rew.cpu().numpy() - d["reward"])
     assert (eo[ok] < 3e-4).mean() > 0.99 and np.median(eo) < 1e-5
     assert (er[ok] < 3e-4).mean() > 0.99
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,task,nb,ny,max_steps", HW_FILES)
+def test_cuda_ssl_hw_env_step_vs_reference(engine, name, task, nb, ny, max_steps):
+    """SSLDribbling-v0 / SSLPassEndurance-v0 recorded from the unmodified reference classes,
+    replayed through the fused CUDA step (k_ssl_hw_env_step)."""
+    import torch
+    d = _load(name)
+    T = len(d["reward"])
+    R = nb + ny
+    g = engine.BatchedWorld(1, 2, nb, ny, 25, T)
+    g.set_raw(d["raw_before"].astype(np.float32))
+    g.steps[:T] = torch.tensor(np.maximum(d["steps_before"], 1), dtype=torch.int32).cuda()
+    g.prev_pot[:T] = torch.tensor(d["counter_before"], dtype=torch.float32).cuda()
+    cg = torch.zeros(T, R, 8, device="cuda")
+    obs, rew, done, trunc = g.ssl_env_step(task, d["action"].astype(np.float32), auto_reset=False,
+                                           max_steps=max_steps, cmds_out=cg)
+    assert np.abs(cg.cpu().numpy().reshape(T, -1) - d["cmds"]).max() < 1e-4
+    # a recorded frame may sit within fp32 rounding of a decision boundary; allow <= 1 flip
+    assert (done.cpu().numpy() != d["done"]).sum() <= 1
+    ok = done.cpu().numpy() == d["done"]
+    eo = np.abs(obs.cpu().numpy() - d["obs"]).max(axis=1)
+    er = np.abs(rew.cpu().numpy() - d["reward"])
+    assert (eo[ok] < 3e-4).mean() > 0.99 and np.median(eo) < 1e-5
+    assert (er[ok] < 3e-4).mean() > 0.99
+    assert (g.prev_pot[:T].cpu().numpy()[ok] == d["counter_after"][ok]).mean() > 0.99

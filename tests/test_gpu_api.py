@@ -132,13 +132,16 @@ def test_fused_vec_env_api_and_host_path(engine):
     f = env.frame
     assert f.ball.x.shape == (n,) and len(f.robots_blue) == 3
     with pytest.raises(KeyError):
-        envs.make("SSLDribbling-v0")
-    for eid, od in (("SSLStaticDefenders-v0", 24), ("SSLContestedPossession-v0", 14)):
+        envs.make("SSLGoToBall-v0")
+    for eid, od, ad, key in (("SSLStaticDefenders-v0", 24, 5, "collision"), ("SSLContestedPossession-v0", 14, 5, "collision"),
+                             ("SSLDribbling-v0", 21, 4, None), ("SSLPassEndurance-v0", 16, 3, "reversed_dist")):
         e = envs.make(eid, num_envs=70)
         o, _ = e.reset()
         assert o.shape == (70, od)
-        o, r, d, tr, i = e.step(torch.zeros(70, 5, device="cuda"))
-        assert o.shape == (70, od) and "collision" in i
+        o, r, d, tr, i = e.step(torch.zeros(70, ad, device="cuda"))
+        assert o.shape == (70, od) and (key is None or key in i)
+        o2, r2, d2, t2 = e.step_host(np.zeros((70, ad), dtype=np.float32))
+        assert o2.shape == (70, od)
         e.close()
 
 

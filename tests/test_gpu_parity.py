@@ -216,6 +216,86 @@ def test_ssl_env_step_parity(engine, oracle, task, nb, ny, max_steps):
     print("worst", worst, "resets", n_done, "infrared steps", n_infra)
 
 
+@pytest.mark.parametrize("task,nb,ny,max_steps", [(3, 1, 4, 40), (4, 2, 0, 40)])
+def test_ssl_hw_env_step_parity(engine, oracle, task, nb, ny, max_steps):
+    """Fused SSLDribbling-v0 / SSLPassEndurance-v0 step vs the oracle, re-synced each step, with
+    scripted scenes (checkpoint crossings, passes into the receiver's mouth) and short episodes so
+    that rewards, every done branch and the on-device auto-reset placement are exercised."""
+    E, O = engine, oracle
+    n, R = 4096, nb + ny
+    nact = 4 if task == 3 else 3
+    g, o = _worlds(E, O, 1, 2, nb, ny, n, seed=6, env_offset=33)
+    g.task_reset(task)
+    o2 = O.OracleWorld(1, 2, nb, ny, 25, n, seed=6, env_offset=33)
+    o2.task_reset(task)
+    assert raw_diff(g.get_raw().cpu().numpy(), o2.get_raw(), R).max() < 1e-5
+    assert np.abs(g.task_reset(task).cpu().numpy() - o2.task_obs(task)).max() < 1e-5
+    rng = np.random.default_rng(12)
+    worst = {"obs": 0.0, "rew": 0.0, "raw": 0.0}
+    n_done = n_rew = 0
+    for it in range(50):
+        raw = g.get_raw().cpu().numpy()
+        k = rng.random(n) < 0.25
+        if task == 3:
+            # the ball about to cross y = 0 inside (or just outside) the x window of checkpoint cc
+            cc = rng.integers(0, 7, n)
+            lo = np.where(cc == 0, -1.0, np.where(cc == 1, -1.5, np.where(cc % 2 == 0, -2.0, -3.0)))
+            hi = np.where(cc == 0, -0.5, np.where(cc == 1, -1.0, np.where(cc % 2 == 0, -1.5, -2.0)))
+            down = (cc % 2 == 0) != (rng.random(n) < 0.25)
+            bx = rng.uniform(lo - 0.1, hi + 0.1)
+            for node in (-0.5, -1.0, -1.5, -2.0):          # not inside a parked robot
+                near = np.abs(bx - node) < 0.13
+                bx[near] = node + np.where(bx[near] < node, -0.13, 0.13)
+            raw[k, 0] = bx[k]
+            raw[k, 1] = np.where(down, 0.004, -0.004)[k]
+            raw[k, 2] = 0.0
+            raw[k, 3] = np.where(down, -2.0, 2.0)[k]
+            raw[k, 4] = (raw[:, 0] + 0.4)[k]; raw[k, 5] = 0.5; raw[k, 7:10] = 0.0
+            out = k & (rng.random(n) < 0.1)
+            raw[out, 4] = 1.02
+            g.set_raw(raw)
+            pp = g.prev_pot[:n].cpu().numpy()
+            pp[k] = cc[k]
+            g.prev_pot[:n] = torch.tensor(pp, device="cuda")
+            st = g.steps[:n].cpu().numpy()
+            g.steps[:n] = torch.tensor(np.maximum(st, 1), device="cuda")
+        else:
+            rx, ry, rth = raw[:, 10], raw[:, 11], raw[:, 12]
+            dd = rng.uniform(0.13, 0.3, n)
+            off = np.where(rng.random(n) < 0.7, rng.uniform(-0.02, 0.02, n), rng.uniform(0.3, 0.6, n))
+            raw[k, 0] = (rx + dd * np.cos(rth) - off * np.sin(rth))[k]
+            raw[k, 1] = (ry + dd * np.sin(rth) + off * np.cos(rth))[k]
+            raw[k, 2] = (-2.5 * np.cos(rth))[k]; raw[k, 3] = (-2.5 * np.sin(rth))[k]
+            g.set_raw(raw)
+        _sync_task(g, o, R)
+        act = rng.uniform(-1, 1, (n, nact)).astype(np.float32)
+        if task == 3:
+            act[k] = 0.0
+        cg = torch.zeros(n, R, 8, device="cuda")
+        obs, rew, done, trunc = g.ssl_env_step(task, act, max_steps=max_steps, cmds_out=cg)
+        oobs, orew, odone, otrunc, ocmd = o.ssl_env_step(task, act, max_steps=max_steps, want_cmds=True)
+        m = o.margin()
+        ok = m >= 5e-6
+        assert np.abs(cg.cpu().numpy() - ocmd)[ok].max() < 1e-4
+        assert (done.cpu().numpy()[ok] == odone[ok]).all()
+        assert (trunc.cpu().numpy() == otrunc).all()
+        n_done += int(odone.sum() + otrunc.sum())
+        n_rew += int((orew > 0.9).sum())
+        e_obs = np.abs(obs.cpu().numpy() - oobs).max(axis=1)
+        e_rew = np.abs(rew.cpu().numpy() - orew)
+        e_raw = raw_diff(g.get_raw().cpu().numpy(), o.get_raw(), R, vel_scale=3.0)
+        e_cnt = np.abs(g.prev_pot[:n].cpu().numpy() - o.get_task_state()["prev_pot"])
+        worst["obs"] = max(worst["obs"], check_close(e_obs, m, "obs it=%d" % it, max_flagged=0.05)[0])
+        worst["rew"] = max(worst["rew"], check_close(e_rew, m, "reward it=%d" % it, max_flagged=0.05)[0])
+        worst["raw"] = max(worst["raw"], check_close(e_raw, m, "state it=%d" % it, max_flagged=0.05)[0])
+        check_close(e_cnt, m, "task counter it=%d" % it, max_flagged=0.05)
+        if task == 4:
+            e_inf = np.abs(g.info[:2, :n].t().cpu().numpy() - o.get_task_state()["info"][:, :2]).max(axis=1)
+            check_close(e_inf, m, "reward_shaping_total it=%d" % it, tol=2e-4, max_flagged=0.05)
+    assert n_done > n and n_rew > n // 8, (n_done, n_rew)
+    print("worst", worst, "resets", n_done, "rewards", n_rew)
+
+
 def test_batch_vs_single_and_shard_invariance(engine):
     """env i of a batch == the same env alone; results do not depend on the sharding."""
     E = engine
