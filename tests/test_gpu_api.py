@@ -236,3 +236,21 @@ def test_preset_kernel_is_selected_and_matches_the_generic_one(engine, monkeypat
         assert torch.equal(ow[3], og[3])
         bad += int((~row_ok).sum())
     assert bad <= 4, bad
+
+
+def test_host_step_equals_the_device_step_at_a_lane_per_match_size(engine):
+    """rs_vss_env_step_host (pinned staging, packed D2H) vs the device-tensor step, bit-exact, at
+    a world size that runs the lane-per-match kernels with a ragged last warp."""
+    from rsoccer_b200 import envs
+    n = 20001
+    env = envs.make("VSS-v0", num_envs=n, seed=8, max_episode_steps=7)
+    ref = envs.make("VSS-v0", num_envs=n, seed=8, max_episode_steps=7)
+    env.reset(); ref.reset()
+    g = torch.Generator().manual_seed(1)
+    for t in range(20):
+        a = torch.rand(n, 2, generator=g) * 2 - 1
+        o1, r1, d1, t1, _ = env.step(a.cuda())
+        o2, r2, d2, t2 = ref.step_host(a.numpy())
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy(), d2) and np.array_equal(t1.cpu().numpy(), t2)
+    assert torch.equal(env.world.get_raw(), ref.world.get_raw()) and env.world.t == ref.world.t
