@@ -379,20 +379,42 @@ struct PairDispatch {
 // lexicographic order, the oracle's Gauss-Seidel order), and reads the scene back.  Different
 // lanes resolve different pairs in the same pass.
 //   q[b]  = (x, y, vx, vy) of body b: receives impulses and position corrections
-//   p0[b] = (x, y, omega, -) at phase start: every contact of the phase is detected on these
+//   p0    = (x, y) and omega of every body at phase start: every contact of the phase is detected on these
 template <int R> __host__ __device__ constexpr uint64_t rr_table(bool second) {
     uint64_t t = 0;
     for (int k = 0; k < R * (R - 1) / 2; ++k) t |= (uint64_t)(second ? rr_pair_j<R>(k) : rr_pair_i<R>(k)) << (3 * k);
     return t;
 }
+// per pair type (0 = ball pair, 1 = robot pair): contact distance, lever arm of the surface
+// velocity, (1 + e) / mass sum, impulse -> velocity of S and F, friction, correction split of S and F
+template <class PP> struct ContactTab {
+    float rs, rc, kn, wS, wF, mu, gS, gF;
+};
+template <class PP>
+__device__ __forceinline__ ContactTab<PP> contact_tab(const PP &P, const bool ball) {
+    ContactTab<PP> t;
+    t.rs = ball ? P.rs_br : P.rs_rr;
+    t.rc = ball ? P.rbt_r : 0.0f;
+    t.kn = ball ? (1.0f + P.e_ball_rbt) * P.inv_wsum : (1.0f + P.e_rbt_rbt) * 0.5f;
+    t.wS = ball ? P.wb : 1.0f; t.wF = ball ? P.wr : 1.0f;
+    t.mu = ball ? P.mu_ball_rbt : 0.0f;
+    t.gS = ball ? P.fb : 0.5f; t.gF = ball ? P.fr : 0.5f;
+    return t;
+}
 template <int RT, class PP>
 __device__ __forceinline__ void contacts_via_smem(const PP &P, Scene<RT> &s, uint32_t m, float4 *q, float4 *p0, const int pitch) {
     static_assert(RT >= 1 && RT <= 7, "3-bit body indices, 21 robot pairs in 63 bits");
-    q[0] = make_float4(s.bx, s.by, s.bvx, s.bvy); p0[0] = make_float4(s.bx, s.by, 0.0f, 0.0f);
+    // q[b] straight from the register quads of the scene; the phase-start copy as (x, y) pairs and
+    // the angular velocities as scalars (no register shuffling to build (x, y, omega, -) quads)
+    const int lane = threadIdx.x & 31;               // q / p0 point at this lane's float4 column of its warp's region
+    float2 *const pxy = reinterpret_cast<float2 *>(p0 - lane) + lane;
+    float *const pom = reinterpret_cast<float *>(p0 - lane + (RT + 1) * pitch / 2) + lane;
+    q[0] = make_float4(s.bx, s.by, s.bvx, s.bvy); pxy[0] = make_float2(s.bx, s.by);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
         q[(r + 1) * pitch] = make_float4(s.x[r], s.y[r], s.vx[r], s.vy[r]);
-        p0[(r + 1) * pitch] = make_float4(s.x[r], s.y[r], s.om[r], 0.0f);
+        pxy[(r + 1) * pitch] = make_float2(s.x[r], s.y[r]);
+        pom[(r + 1) * pitch] = s.om[r];
     }
     constexpr uint64_t TI = rr_table<RT>(false), TJ = rr_table<RT>(true);
     do {
@@ -402,31 +424,30 @@ __device__ __forceinline__ void contacts_via_smem(const PP &P, Scene<RT> &s, uin
         const bool ball = p < RT;
         const int k3 = 3 * (p - RT);
         const int F = ball ? p + 1 : 1 + (int)((TI >> k3) & 7u), S = ball ? 0 : 1 + (int)((TJ >> k3) & 7u);
-        const float4 pf = p0[F * pitch], ps = p0[S * pitch];
+        const ContactTab<PP> T = contact_tab(P, ball);
+        const float2 pf = pxy[F * pitch], ps = pxy[S * pitch];
+        const float omf = pom[F * pitch];
         float4 qf = q[F * pitch], qs = q[S * pitch];
         const float dx = ps.x - pf.x, dy = ps.y - pf.y;
         const float d2 = dx * dx + dy * dy;
         const float inv = rsqrtf(d2);
         const bool ok = d2 > 1e-12f;
         const float nx = ok ? dx * inv : 1.0f, ny = ok ? dy * inv : 0.0f, d = ok ? d2 * inv : 0.0f;
-        const float pen = (ball ? P.rs_br : P.rs_rr) - d;
-        const float rc = ball ? P.rbt_r : 0.0f;
-        const float rcx = nx * rc, rcy = ny * rc;
-        const float sx = qf.z - pf.z * rcy, sy = qf.w + pf.z * rcx;   // F's surface velocity at the contact
+        const float pen = T.rs - d;
+        const float rcx = nx * T.rc, rcy = ny * T.rc;
+        const float sx = qf.z - omf * rcy, sy = qf.w + omf * rcx;     // F's surface velocity at the contact
         const float relx = qs.z - sx, rely = qs.w - sy;
         const float vn = fminf(relx * nx + rely * ny, 0.0f);          // separating: every impulse below is +-0
         // ball pair: Jn = -(1 + e) vn / (wb + wr), dv = Jn w n.  robot pair: equal masses, dv = -(1 + e) vn / 2 n
-        const float Jn = -(1.0f + (ball ? P.e_ball_rbt : P.e_rbt_rbt)) * vn * (ball ? P.inv_wsum : 0.5f);
-        const float wS = ball ? P.wb : 1.0f, wF = ball ? P.wr : 1.0f;
-        qs.z += Jn * wS * nx; qs.w += Jn * wS * ny;
-        qf.z -= Jn * wF * nx; qf.w -= Jn * wF * ny;
+        const float Jn = -T.kn * vn;
+        qs.z += Jn * T.wS * nx; qs.w += Jn * T.wS * ny;
+        qf.z -= Jn * T.wF * nx; qf.w -= Jn * T.wF * ny;
         const float tx = -ny, ty = nx;
         const float vt = relx * tx + rely * ty;
-        const float mu = ball ? P.mu_ball_rbt : 0.0f;
-        const float Jt = clampf(-vt * P.inv_wsum, -mu * Jn, mu * Jn);
-        qs.z += Jt * wS * tx; qs.w += Jt * wS * ty;
-        qf.z -= Jt * wF * tx; qf.w -= Jt * wF * ty;
-        const float gS = pen * (ball ? P.fb : 0.5f), gF = pen * (ball ? P.fr : 0.5f);
+        const float Jt = clampf(-vt * P.inv_wsum, -T.mu * Jn, T.mu * Jn);
+        qs.z += Jt * T.wS * tx; qs.w += Jt * T.wS * ty;
+        qf.z -= Jt * T.wF * tx; qf.w -= Jt * T.wF * ty;
+        const float gS = pen * T.gS, gF = pen * T.gF;
         qs.x += gS * nx; qs.y += gS * ny;
         qf.x -= gF * nx; qf.y -= gF * ny;
         q[F * pitch] = qf; q[S * pitch] = qs;
