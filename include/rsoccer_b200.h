@@ -143,8 +143,9 @@ int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, vo
  * action -> wheel speeds, physics, observation, reward, done, TimeLimit
  * truncation, reward_shaping_total, masked auto-reset.
  *  d_actions [N][2] in [-1,1]; d_normals (nullable) [N][2(R-1)] standard normals
- *  that replace the on-device Philox draw (parity harness); d_obs [N][40];
- *  d_reward [N]; d_done [N]; d_trunc [N]; d_cmds_out (nullable) [N][R][2]. */
+ *  that replace the on-device Philox draw (parity harness); d_obs [N][40], 16-byte aligned
+ *  (d_actions 8-byte aligned); d_reward [N]; d_done [N]; d_trunc [N]; d_cmds_out (nullable)
+ *  [N][R][2]. */
 int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals, int auto_reset,
                     int max_steps, float *d_obs, float *d_reward, uint8_t *d_done,
                     uint8_t *d_trunc, float *d_cmds_out, void *stream);
