@@ -193,6 +193,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # rank 0's stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     N, M = args.envs, max(1, args.worlds)
