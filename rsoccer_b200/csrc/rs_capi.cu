@@ -76,9 +76,11 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         load_scene<R>(P, S, e, s);
         const int st = S.steps[e];
         float prev = S.prev[e];
-        float info[RS_VSS_INFO];
-#pragma unroll
-        for (int i = 0; i < RS_VSS_INFO; ++i) info[i] = S.info[(size_t)i * S.np + e];
+        // reward_shaping_total is never loaded: the six accumulators are zeroed by a store at the
+        // first step of an episode and updated by fire-and-forget reductions (RED.ADD.F32, one
+        // add per word and step: same rounding as load-add-store) -- move / ball_grad / energy every
+        // step, goal_score / goals_blue / goals_yellow only when a goal is scored.  36 of the 640
+        // bytes a step used to move per env.
         float2 ou[R - 1];
 #pragma unroll
         for (int r = 1; r < R; ++r) ou[r - 1] = S.ou[(size_t)(r - 1) * S.np + e];
@@ -140,15 +142,17 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         bool has_prev = (st >> 24) & 1;
         if (steps == 0) {
 #pragma unroll
-            for (int i = 0; i < RS_VSS_INFO; ++i) info[i] = 0.0f;
+            for (int i = 0; i < RS_VSS_INFO; ++i) S.info[(size_t)i * S.np + e] = 0.0f;
         }
         steps += 1;                                                 // vss_gym_base.py:73
 
         // ---- _calculate_reward_and_done, vss_gym.py:144-192
         float rew; bool goal = false;
-        if (s.bx > P.half_len) { info[0] += 1.0f; info[4] += 1.0f; rew = 10.0f; goal = true; }
-        else if (s.bx < -P.half_len) { info[0] -= 1.0f; info[5] += 1.0f; rew = -10.0f; goal = true; }
-        else {
+        if (s.bx > P.half_len) {
+            atomicAdd(&S.info[e], 1.0f); atomicAdd(&S.info[(size_t)4 * S.np + e], 1.0f); rew = 10.0f; goal = true;
+        } else if (s.bx < -P.half_len) {
+            atomicAdd(&S.info[e], -1.0f); atomicAdd(&S.info[(size_t)5 * S.np + e], 1.0f); rew = -10.0f; goal = true;
+        } else {
             const float length_cm = 2.0f * P.half_len * 100.0f, hl = P.half_len + P.goal_depth;
             const float dx_d = (hl + s.bx) * 100.0f, dx_a = (hl - s.bx) * 100.0f, dy = s.by * 100.0f;
             const float pot = ((-sqrtf(dx_a * dx_a + 2.0f * dy * dy) + sqrtf(dx_d * dx_d + 2.0f * dy * dy)) / length_cm - 1.0f) * 0.5f;
@@ -160,12 +164,12 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
             const float move = clampf((rx * rinv * s.vx[0] + ry * rinv * s.vy[0]) * (1.0f / 0.4f), -5.0f, 5.0f);
             const float energy = -(fabsf(wl0) + fabsf(wr0));
             rew = 0.2f * move + 0.8f * grad + 2e-4f * energy;
-            info[1] += 0.2f * move; info[2] += 0.8f * grad; info[3] += 2e-4f * energy;
+            atomicAdd(&S.info[(size_t)1 * S.np + e], 0.2f * move);
+            atomicAdd(&S.info[(size_t)2 * S.np + e], 0.8f * grad);
+            atomicAdd(&S.info[(size_t)3 * S.np + e], 2e-4f * energy);
         }
         const bool tr = steps >= A.max_steps;                       // TimeLimit, __init__.py:4
         A.reward[e] = rew; A.done[e] = goal ? 1 : 0; A.trunc[e] = tr ? 1 : 0;
-#pragma unroll
-        for (int i = 0; i < RS_VSS_INFO; ++i) S.info[(size_t)i * S.np + e] = info[i];
 
         if (A.auto_reset) {
             // rare (one match in ~6 000 per step) but on the critical path of the kernel: the
