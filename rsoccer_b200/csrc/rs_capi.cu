@@ -71,7 +71,9 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
     }
 #endif
     if (e < S.n) {
-        // ---- every global load of the step is issued first ...
+        // ---- every global load of the step is issued first: the step counter ahead of the state,
+        // so that it is not queued behind 100 KB of requests per SM and Philox can start at once
+        const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
         Scene<R> s;
         load_scene<R>(P, S, e, s);
         const int st = S.steps[e];
@@ -85,7 +87,6 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 #pragma unroll
         for (int r = 1; r < R; ++r) ou[r - 1] = S.ou[(size_t)(r - 1) * S.np + e];
         const float2 act = A.actions[e];
-        const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
 
         // ---- ... and the OU noise (Philox + Box-Muller, ~15 % of the instructions, needs
         // only the env id and the step counter) is computed while they are in flight
