@@ -72,3 +72,16 @@ def test_product_never_imports_the_oracle():
                 assert "oracle" not in txt.lower().replace("the oracle", "").replace("oracle/", "").replace(
                     "oracle's", "").replace("oracle of", "") or "import" not in txt or all(
                     "oracle" not in ln for ln in txt.splitlines() if ln.strip().startswith(("import", "from", "#include"))), f
+
+
+def test_argument_validation_needs_no_device(lib):
+    """bad sizes / unknown worlds are rejected before any CUDA call; rs_task_act_dim is a pure
+    table of the reference action spaces (vss_gym.py:64, static_defenders.py:54,
+    dribbling.py:50-51, pass_endurance.py:53)."""
+    L = lib.lib()
+    h = ctypes.c_void_p()
+    for args in ((0, 0, 3, 3, 25, 0), (0, 0, 3, 3, 0, 4), (0, 7, 3, 3, 25, 4), (1, 2, 12, 11, 25, 4), (2, 0, 1, 1, 25, 4)):
+        assert L.rs_create(*args, -1, 0, 0, ctypes.byref(h)) == -1 and not h.value       # RS_E_INVALID
+    assert L.rs_create(0, 0, 3, 3, 25, 4, -1, 0, 2 ** 32, ctypes.byref(h)) == -1          # env ids must fit 32 bits
+    assert [L.rs_task_act_dim(t) for t in range(5)] == [2, 5, 5, 4, 3]
+    assert L.rs_task_act_dim(9) < 0 and b"unknown task" in L.rs_last_error()

@@ -316,3 +316,29 @@ def test_batch_vs_single_and_shard_invariance(engine):
         assert torch.equal(rb, torch.cat([rl, rh]))
         assert torch.equal(db, torch.cat([dl, dh]))
     assert torch.equal(big.get_raw(), torch.cat([lo.get_raw(), hi.get_raw()]))
+
+
+@pytest.mark.parametrize("n", [1, 33, 130])
+def test_tiny_and_ragged_worlds_all_tasks(engine, oracle, n):
+    """one match, one warp plus one lane, two ragged CTAs: every fused task step vs the oracle
+    (both kernel mappings through the `engine` fixture), 12 steps with 5-step episodes."""
+    E, O = engine, oracle
+    rng = np.random.default_rng(n)
+    for task, kind, ft, nb, ny, nact in ((0, 0, 0, 3, 3, 2), (1, 1, 2, 1, 6, 5), (2, 1, 2, 1, 1, 5), (3, 1, 2, 1, 4, 4), (4, 1, 2, 2, 0, 3)):
+        R = nb + ny
+        g, o = _worlds(E, O, kind, ft, nb, ny, n, seed=21, env_offset=5)
+        g.task_reset(task)
+        for it in range(12):
+            _sync_task(g, o, R)
+            act = rng.uniform(-1, 1, (n, nact)).astype(np.float32)
+            if task == 0:
+                obs, rew, done, trunc = g.vss_env_step(act, max_steps=5)
+                oobs, orew, odone, otrunc = o.vss_env_step(act, max_steps=5)
+            else:
+                obs, rew, done, trunc = g.ssl_env_step(task, act, max_steps=5)
+                oobs, orew, odone, otrunc = o.ssl_env_step(task, act, max_steps=5)
+            ok = o.margin() >= 5e-6
+            assert obs.shape == oobs.shape and (trunc.cpu().numpy() == otrunc).all()
+            assert (done.cpu().numpy()[ok] == odone[ok]).all()
+            assert np.abs(obs.cpu().numpy() - oobs)[ok].max(initial=0.0) < 2e-4
+            assert np.abs(rew.cpu().numpy() - orew)[ok].max(initial=0.0) < 2e-4
