@@ -182,10 +182,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
                 need &= need - 1;
                 const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
                 const uint32_t env_src = A.env_offset + (uint32_t)(w0 + src);
-                const uint4 blk = philox4x32_10(make_uint4(env_src, t_now, RS_STREAM_AUTORESET, (uint32_t)(tid & 31)), key);
-                __syncwarp(live);
-                reinterpret_cast<uint4 *>(wtile)[tid & 31] = blk;
-                __syncwarp(live);
+                warp_placement_words(reinterpret_cast<uint32_t *>(wtile), live, A.seed, env_src, t_now);
                 if ((tid & 31) == src) {
                     PlaceStream g{reinterpret_cast<const uint32_t *>(wtile), wrows, key, env_src, t_now, 0};
                     vss_place_stream<R>(P, g, s);
@@ -227,6 +224,7 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     constexpr int EPB = BS / L, MPW = 32 / L;
     static_assert(RS_AUX_INFO + RS_VSS_INFO == L, "one task word per lane");
     __shared__ __align__(128) float tile[EPB * NOBS];
+    __shared__ __align__(16) uint32_t pbuf[BS / 32][128 + MPW * (2 + 3 * R)];      // auto-reset placement (rs_lanes.cuh)
     const int tid = threadIdx.x;
     const int b = tid & (L - 1);                               // body of this lane
     const int el = tid / L;                                    // match within the CTA
@@ -324,14 +322,8 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
         if (b == RS_AUX_STEPS) out = reset ? 0u : ((uint32_t)steps | ((has_prev ? 1u : 0u) << 24));
         if (valid) S.aux[(size_t)b * S.np + e] = out;
     }
-    if (reset) {        // rare, uniform within the group: every lane draws the placement, keeps its body
-        Scene<0> tmp;
-        vss_place<0>(P, Rng(A.seed, gid, t_now, RS_STREAM_AUTORESET), tmp);
-        if (b == 0) { s.x = tmp.bx; s.y = tmp.by; }
-        else if (is_robot) { s.x = tmp.x[b - 1]; s.y = tmp.y[b - 1]; s.th = tmp.th[b - 1]; }
-        s.vx = 0.0f; s.vy = 0.0f; s.om = 0.0f;
-        a = make_float2(0.0f, 0.0f);
-    }
+    lanes_reset_place<RS_TASK_VSS, R, L>(P, pbuf[tid >> 5], reset, valid, b, is_robot, gid, A.seed, t_now, s);
+    if (reset) { s.vx = 0.0f; s.vy = 0.0f; s.om = 0.0f; a = make_float2(0.0f, 0.0f); }
     __syncwarp();
     // ---- stores
     if (valid) {
@@ -460,19 +452,35 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         A.reward[e] = rew; A.done[e] = dn ? 1 : 0; A.trunc[e] = tr ? 1 : 0;
 #pragma unroll
         for (int i = 0; i < RS_SSL_INFO; ++i) S.info[(size_t)i * S.np + e] = info[i];
-        if (A.auto_reset && (dn || tr)) {
-            Scene<0> tmp;
-            task_place<TASK, 0>(P, Rng(A.seed, A.env_offset + (uint32_t)e, t_now, RS_STREAM_AUTORESET), tmp);
-            s.bx = tmp.bx; s.by = tmp.by; s.bvx = 0.0f; s.bvy = 0.0f;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                s.x[r] = tmp.x[r]; s.y[r] = tmp.y[r]; s.th[r] = tmp.th[r];
-                s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+        if (TASK == RS_TASK_SSL_CONTESTED_POSSESSION) {
+            // two draws, no rejection loop: the scalar placement is cheaper than a warp-wide one (7.19 vs 7.34 us)
+            if (A.auto_reset && (dn || tr)) {
+                const PlaceStream g{nullptr, 0, make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)),
+                                    A.env_offset + (uint32_t)e, t_now, 0};
+                place_from_stream<TASK, R>(P, g, s);
+                steps = 0;
             }
-            steps = 0;
+        } else if (A.auto_reset) {
+            // warp-cooperative placement of the ending matches (see k_vss_env_step); the word buffer is
+            // this warp's part of the observation tile, not yet written
+            uint32_t *const wbuf = reinterpret_cast<uint32_t *>(tile + (tid & ~31) * NOBS);
+            static_assert(32 * NOBS >= 128, "128 placement words fit the warp's observation rows");
+            unsigned need = __ballot_sync(live, dn || tr);
+            while (need) {
+                const int src = __ffs((int)need) - 1;
+                need &= need - 1;
+                const uint32_t env_src = A.env_offset + (uint32_t)(w0 + src);
+                warp_placement_words(wbuf, live, A.seed, env_src, t_now);
+                if ((tid & 31) == src) {
+                    const PlaceStream g{wbuf, wrows, make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)), env_src, t_now, 0};
+                    place_from_stream<TASK, R>(P, g, s);
+                    steps = 0;
+                }
+            }
         }
         store_scene<R>(P, S, e, s);
         S.steps[e] = steps;
+        __syncwarp(live);          // the rows below overlay the placement words an ending lane may still read
         ssl_obs<NB, NY>(P, s, tile + tid * NOBS);
         step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
     }
@@ -626,6 +634,7 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     constexpr int NW = RS_AUX_INFO + RS_SSL_INFO, KW = (NW + L - 1) / L;
     static_assert(NB == 1 && R + 1 <= L, "the benchmarked SSL tasks have one agent, blue 0");
     __shared__ __align__(128) float tile[EPB * NOBS];
+    __shared__ __align__(16) uint32_t pbuf[BS / 32][128 + MPW * (2 + 3 * R)];      // auto-reset placement (rs_lanes.cuh)
     const int tid = threadIdx.x;
     const int b = tid & (L - 1);
     const int el = tid / L;
@@ -734,13 +743,8 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
         if (w == RS_AUX_STEPS) out = reset ? 0u : (uint32_t)steps;
         if (valid && w < NW && w != RS_AUX_PREV) S.aux[(size_t)w * S.np + e] = out;
     }
-    if (reset) {
-        Scene<0> tmp;
-        task_place<TASK, 0>(P, Rng(A.seed, A.env_offset + (uint32_t)ec, t_now, RS_STREAM_AUTORESET), tmp);
-        if (b == 0) { s.x = tmp.bx; s.y = tmp.by; }
-        else if (is_robot) { s.x = tmp.x[b - 1]; s.y = tmp.y[b - 1]; s.th = tmp.th[b - 1]; }
-        s.vx = 0.0f; s.vy = 0.0f; s.om = 0.0f;
-    }
+    lanes_reset_place<TASK, R, L>(P, pbuf[tid >> 5], reset, valid, b, is_robot, A.env_offset + (uint32_t)ec, A.seed, t_now, s);
+    if (reset) { s.vx = 0.0f; s.vy = 0.0f; s.om = 0.0f; }
     __syncwarp();
     if (valid) lanes_store<L>(S, R, b, e, s);
     // ---- observation row (static_defenders.py:90-112): ball 4, blue 8 (with infrared), yellow x y

@@ -143,6 +143,68 @@ __device__ __forceinline__ void vss_place_stream(const PP &P, PlaceStream g, Sce
         s.th[r] = wrap_pi(g.uniform(0.0f, 360.0f) * (1.0f / RS_DEG_F));
     }
 }
+// static_defenders.py:214-254 fed from a PlaceStream (see vss_place_stream): same draws, same results
+template <int R, class PP>
+__device__ __forceinline__ void ssl_sd_place_stream(const PP &P, PlaceStream g, Scene<R> &s) {
+    const float hl = P.half_len, hw = P.half_wid;
+    s.x[0] = 0.0f; s.y[0] = 0.0f; s.th[0] = 0.0f; s.vx[0] = 0.0f; s.vy[0] = 0.0f; s.om[0] = 0.0f;
+#pragma unroll 1
+    for (int tries = 0; tries < 64; ++tries) {
+        s.bx = g.uniform(0.2f, hl - 0.1f); s.by = g.uniform(-hw + 0.1f, hw - 0.1f);
+        if (!(s.bx > hl - P.pen_len && fabsf(s.by) < P.half_pen_wid)) break;
+    }
+    s.bvx = 0.0f; s.bvy = 0.0f;
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        float x = 0.0f, y = 0.0f;
+#pragma unroll 1
+        for (int tries = 0; tries < 64; ++tries) {
+            x = g.uniform(0.2f, hl - 0.1f); y = g.uniform(-hw + 0.1f, hw - 0.1f);
+            float dx = x - s.bx, dy = y - s.by;
+            bool ok = !(dx * dx + dy * dy < 0.04f);
+#pragma unroll
+            for (int k = 0; k < r; ++k) {
+                dx = x - s.x[k]; dy = y - s.y[k];
+                if (dx * dx + dy * dy < 0.04f) ok = false;
+            }
+            if (ok) break;
+        }
+        s.x[r] = x; s.y[r] = y; s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+        s.th[r] = wrap_pi(g.uniform(0.0f, 360.0f) * (1.0f / RS_DEG_F));
+    }
+}
+// contested_possession.py:210-227 (two draws)
+template <int R, class PP>
+__device__ __forceinline__ void ssl_cp_place_stream(const PP &P, PlaceStream g, Scene<R> &s) {
+    s.x[0] = 0.0f; s.y[0] = 0.0f; s.th[0] = 0.0f; s.vx[0] = 0.0f; s.vy[0] = 0.0f; s.om[0] = 0.0f;
+    const float ex = g.uniform(P.pen_len, P.half_len - P.pen_len);
+    const float ey = g.uniform(-P.half_pen_wid, P.half_pen_wid);
+    s.bx = ex - 0.1f; s.by = ey; s.bvx = 0.0f; s.bvy = 0.0f;
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        s.x[r] = ex; s.y[r] = ey + 0.5f * (float)(r - 1); s.th[r] = RS_PI_F;
+        s.vx[r] = 0.0f; s.vy[r] = 0.0f; s.om[r] = 0.0f;
+    }
+}
+template <int TASK, int R, class PP>
+__device__ __forceinline__ void place_from_stream(const PP &P, const PlaceStream &g, Scene<R> &s) {
+    if constexpr (TASK == RS_TASK_VSS) vss_place_stream<R>(P, g, s);
+    else if constexpr (TASK == RS_TASK_SSL_STATIC_DEFENDERS) ssl_sd_place_stream<R>(P, g, s);
+    else ssl_cp_place_stream<R>(P, g, s);
+}
+
+// Warp-cooperative draw of the first 4 x navail words of the auto-reset placement stream of the
+// match whose global id is `env_src`: lane j computes Philox block j and writes it to words
+// [4 j, 4 j + 4) of `buf` (shared memory, 128 words per warp).  Every lane in `live` calls.
+__device__ __forceinline__ void warp_placement_words(uint32_t *buf, const unsigned live, const uint64_t seed,
+                                                     const uint32_t env_src, const uint32_t t) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint4 blk = philox4x32_10(make_uint4(env_src, t, RS_STREAM_AUTORESET, (uint32_t)(threadIdx.x & 31)), key);
+    __syncwarp(live);
+    reinterpret_cast<uint4 *>(buf)[threadIdx.x & 31] = blk;
+    __syncwarp(live);
+}
+
 // static_defenders.py:214-254
 template <int RT>
 __device__ __noinline__ void ssl_sd_place(const DevParams &P, Rng g, Scene<RT> &s) {

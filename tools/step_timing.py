@@ -67,7 +67,7 @@ def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=Tr
         elif task == E.TASK_VSS_V0:
             worlds[m].vss_env_step(acts[m], out=outs[m], auto_reset=AUTO_RESET)
         else:
-            worlds[m].ssl_env_step(task, acts[m], out=outs[m])
+            worlds[m].ssl_env_step(task, acts[m], out=outs[m], auto_reset=AUTO_RESET)
 
     M = max(n_worlds, graph_steps)          # steps per captured graph (a multiple of the world count)
     stream = torch.cuda.Stream(device=dev)
