@@ -123,7 +123,7 @@ def cpu_baseline_run(threads, target_seconds, envs=4096):
                       % (envs, steps, dt)}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """--impl reference: the CPU path, all host threads, bounded sample per step."""
     if rank != 0:
         return
@@ -156,10 +156,22 @@ def run_reference(args, rank, world):
                          "sample": "%d envs x %d steps per run, OpenMP %d threads" % (envs, steps, threads)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write to file descriptor 1 behind
+    Python's back (NCCL prints "NCCL version ..." there at communicator creation), so fd 1 is
+    pointed at stderr for the whole run and the JSON line goes to a private copy of the
+    original stdout."""
+    out = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return out
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=24000, help="timed steps (default = 20 episode horizons)")
@@ -181,7 +193,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -193,8 +205,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # rank 0's stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     N, M = args.envs, max(1, args.worlds)
@@ -321,7 +331,7 @@ def main():
                          "avg_launch_us": per_launch_s * 1e6},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
