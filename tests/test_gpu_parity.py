@@ -342,3 +342,57 @@ def test_tiny_and_ragged_worlds_all_tasks(engine, oracle, n):
             assert (done.cpu().numpy()[ok] == odone[ok]).all()
             assert np.abs(obs.cpu().numpy() - oobs)[ok].max(initial=0.0) < 2e-4
             assert np.abs(rew.cpu().numpy() - orew)[ok].max(initial=0.0) < 2e-4
+
+
+@pytest.mark.parametrize("n", [65536, 262144])
+def test_full_size_properties(engine, oracle, n):
+    """BASELINE.json's full sizes (65 536 matches per GPU; 262 144 = config 5's total), through
+    size-independent properties: the whole world == its two halves stepped as separate worlds
+    (bit-exact, auto-reset included), every body stays inside the walls, observations inside the
+    normalisation bounds, and a random sample of 512 matches of the big world replayed alone in
+    the fp64 oracle agrees to the parity tolerance."""
+    E, O = engine, oracle
+    big = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=13)
+    lo = E.BatchedWorld(0, 0, 3, 3, 25, n // 2, seed=13, env_offset=0)
+    hi = E.BatchedWorld(0, 0, 3, 3, 25, n // 2, seed=13, env_offset=n // 2)
+    for w in (big, lo, hi):
+        w.task_reset(E.TASK_VSS_V0)
+    g = torch.Generator(device="cpu").manual_seed(2)
+    rng = np.random.default_rng(4)
+    pick = np.sort(rng.choice(n, 512, replace=False))
+    o = O.OracleWorld(0, 0, 3, 3, 25, 512, seed=13, threads=8)
+    fp = o.field_params()
+    for it in range(24):
+        a = (torch.rand(n, 2, generator=g) * 2 - 1).cuda()
+        if it % 6 == 5:
+            # sampled oracle replay of this step: state, task words and noise of the picked matches
+            raw = big.get_raw()[pick].cpu().numpy().astype(np.float64)
+            st = big.steps[:n][pick].cpu().numpy()
+            ou = big.ou[:, :n, :][:, pick].permute(1, 0, 2).reshape(512, -1).cpu().numpy().astype(np.float64)
+            o.set_raw(raw)
+            o.set_task_state(ou=ou, prev_pot=big.prev_pot[:n][pick].cpu().numpy().astype(np.float64),
+                             has_prev=((st >> 24) & 1).astype(np.int32), steps=(st & 0xFFFFFF).astype(np.int32),
+                             info=np.zeros((512, 9)))
+            ou_before = big.ou[:, :n, :].clone()
+        ob, rb, db, tb = big.vss_env_step(a, max_steps=11)
+        ol, rl, dl, tl = lo.vss_env_step(a[:n // 2], max_steps=11)
+        oh, rh, dh, th = hi.vss_env_step(a[n // 2:], max_steps=11)
+        assert torch.equal(ob, torch.cat([ol, oh])) and torch.equal(rb, torch.cat([rl, rh]))
+        assert torch.equal(db, torch.cat([dl, dh])) and torch.equal(tb, torch.cat([tl, th]))
+        assert bool(torch.isfinite(ob).all()) and float(ob.abs().max()) <= 1.2 + 1e-6
+        if it % 6 == 5:
+            # the OU noise the device drew = (new - (1 - theta dt) old) / (sigma sqrt(dt)): feed it to the oracle
+            z = (big.ou[:, :n, :] - ou_before * (1 - 0.17 * 0.025)) / (0.5 * np.sqrt(0.025))
+            keep = (~(db.bool() | tb.bool()))[pick].cpu().numpy()          # reset matches restart their OU state
+            zs = z[:, pick].permute(1, 0, 2).reshape(512, -1).cpu().numpy().astype(np.float64)
+            oobs, orew, odone, otr = o.vss_env_step(a[pick].cpu().numpy(), normals=zs, auto_reset=False, max_steps=11)
+            ok = keep & (o.margin() >= 5e-6)
+            assert ok.mean() > 0.8
+            assert np.abs(ob[pick].cpu().numpy() - oobs)[ok].max() < 2e-4
+            assert np.abs(rb[pick].cpu().numpy() - orew)[ok].max() < 2e-4
+            assert (db[pick].cpu().numpy()[ok] == odone[ok]).all()
+    raw = big.get_raw()
+    assert torch.equal(raw, torch.cat([lo.get_raw(), hi.get_raw()]))
+    x = raw[:, [0] + [4 + 6 * r for r in range(6)]].abs()
+    y = raw[:, [1] + [5 + 6 * r for r in range(6)]].abs()
+    assert float(x.max()) <= fp["length"] / 2 + fp["goal_depth"] + 1e-6 and float(y.max()) <= fp["width"] / 2 + 1e-6
