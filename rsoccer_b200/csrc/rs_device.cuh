@@ -597,7 +597,7 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
         // (e) pairs, lexicographic; contacts detected on the positions at phase start,
         // velocity impulses applied sequentially, position corrections applied on top of them.
         // A contact is rare per lane (~7 % of the matches have one at any time,
-        // tools/contact_stats.py) but in a warp of 32 matches "some lane has one" holds for
+        // tests/contact_stats.py) but in a warp of 32 matches "some lane has one" holds for
         // ~95 % of the sub-steps, spread over the pairs.  Up to 28 pairs (R <= 7):
         //   1. detection is straight-line: one FFMA pair and one funnel shift per pair (the sign
         //      bit of d^2 - rs^2 is the mask bit), no compare, no branch, full ILP;
