@@ -321,7 +321,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": Ke, "ms_per_step": ms_e2e / Ke,
                     "h2d_bytes_per_step": N * 2 * 4, "d2h_bytes_per_step": N * (40 * 4 + 4 + 1 + 1),
-                    "api": "rs_vss_env_step_host (pinned host buffers, H2D + kernel + one packed D2H + sync)",
+                    "api": "rs_vss_env_step_host (pinned host buffers: actions read over PCIe by the kernel, one packed D2H of obs/reward/done/trunc, sync)",
                     "pcie_gbs": (N * 2 * 4 + N * (40 * 4 + 4 + 1 + 1)) / (ms_e2e * 1e-3 / Ke) / 1e9},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
