@@ -92,6 +92,25 @@ struct Drive {
 };
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// Packed fp32x2 arithmetic of sm_100 (SASS FFMA2 / FADD2 / FMUL2; a scalar register or an
+// immediate broadcasts into both halves, negation is an operand modifier): two IEEE results per
+// issued instruction, each half rounded exactly like the scalar instruction.  The step kernels
+// are bound by issue slots and dependent latency, not by the FMA pipe, so every
+// (x, y) / (vx, vy) operation of a body -- the halves of the register quad its state was loaded
+// into -- is issued as one instruction.  RS_X_NOPACK* = scalar form (tuning knobs).
+// a - b as ONE instruction: written as add(a, -b) the compiler keeps a negated copy of every body that enters
+// several pairs (two FADD each) instead of using the operand modifier
+__device__ __forceinline__ float2 pk_sub(const float2 a, const float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 pa, pb, pr;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\t"
+        "sub.rn.ftz.f32x2 pr, pa, pb;\n\tmov.b64 {%0, %1}, pr;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 pk_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 pk_fma(const float2 a, const float2 b, const float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 pk_bc(const float a) { return make_float2(a, a); }
 __device__ __forceinline__ float wrap_pi(float a) {
     if (a > RS_PI_F) a -= 2.0f * RS_PI_F; else if (a <= -RS_PI_F) a += 2.0f * RS_PI_F;
     return a;
@@ -225,7 +244,7 @@ template <class PP>
 __device__ __forceinline__ void vss_walls(const PP &P, const float r, const float e, float &x, float &y, float &vx, float &vy) {
     const float Lh = wall_lx(P), Gh = wall_ly(P);
     const float XO = P.x_out - r, XL = Lh - r, YO = P.y_out - r, YL = Gh - r;      // loop invariants / immediates
-    const float dx = fabsf(x) - Lh, dy = fabsf(y) - Gh;
+    const float dx = fabsf(x) - Lh, dy = fabsf(y) - Gh;      // |.| is an operand modifier of FADD, not of FADD2
     float xlim = dy < 0.0f ? XO : XL, ylim = dx < 0.0f ? YO : YL;
     // both within r of a face AND on the same side of both faces (a robot leaning on the end
     // wall is within r of both, but outside one and inside the other: no branch for it)
@@ -246,7 +265,12 @@ __device__ __forceinline__ void vss_walls(const PP &P, const float r, const floa
             if (dy < dx) xlim = XO; else ylim = YO;
         }
     }
+#ifndef RS_X_NOPACK_WALL
+    const float2 oo = pk_mul(make_float2(vx, vy), make_float2(x, y));
+    const float ox = oo.x, oy = oo.y;                     // > 0: moving outward
+#else
     const float ox = vx * x, oy = vy * y;                 // > 0: moving outward
+#endif
     const bool hx = fabsf(x) > xlim, hy = fabsf(y) > ylim;
     x = fmaxf(fminf(x, xlim), -xlim); y = fmaxf(fminf(y, ylim), -ylim);
     if (hx && ox > 0.0f) vx = wall_bounce(P, e, vx);
@@ -428,6 +452,28 @@ __device__ __forceinline__ void contacts_via_smem(const PP &P, Scene<RT> &s, uin
         const float2 pf = pxy[F * pitch], ps = pxy[S * pitch];
         const float omf = pom[F * pitch];
         float4 qf = q[F * pitch], qs = q[S * pitch];
+#ifndef RS_X_NOPACK_CONTACT
+        const float2 dd = pk_sub(ps, pf);
+        const float d2 = dd.x * dd.x + dd.y * dd.y;
+        const float inv = rsqrtf(d2);
+        const bool ok = d2 > 1e-12f;
+        float2 n = pk_mul(dd, pk_bc(inv));
+        n.x = ok ? n.x : 1.0f; n.y = ok ? n.y : 0.0f;
+        const float d = ok ? d2 * inv : 0.0f;
+        const float pen = T.rs - d;
+        const float2 rc = pk_mul(n, pk_bc(T.rc));
+        const float2 rel = pk_sub(make_float2(qs.z, qs.w), make_float2(qf.z - omf * rc.y, qf.w + omf * rc.x));   // S - F's surface velocity
+        const float vn = fminf(rel.x * n.x + rel.y * n.y, 0.0f);       // separating: every impulse below is +-0
+        // ball pair: Jn = -(1 + e) vn / (wb + wr), dv = Jn w n.  robot pair: equal masses, dv = -(1 + e) vn / 2 n
+        const float Jn = -T.kn * vn;
+        const float vt = rel.y * n.x - rel.x * n.y;                    // tangent (-ny, nx)
+        const float Jt = clampf(-vt * P.inv_wsum, -T.mu * Jn, T.mu * Jn);
+        float2 vs = pk_fma(n, pk_bc(Jn * T.wS), make_float2(qs.z, qs.w)), vf = pk_fma(n, pk_bc(-Jn * T.wF), make_float2(qf.z, qf.w));
+        const float jS = Jt * T.wS, jF = Jt * T.wF;
+        vs.x -= jS * n.y; vs.y += jS * n.x; vf.x += jF * n.y; vf.y -= jF * n.x;
+        const float2 xs = pk_fma(n, pk_bc(pen * T.gS), make_float2(qs.x, qs.y)), xf = pk_fma(n, pk_bc(-pen * T.gF), make_float2(qf.x, qf.y));
+        qs = make_float4(xs.x, xs.y, vs.x, vs.y); qf = make_float4(xf.x, xf.y, vf.x, vf.y);
+#else
         const float dx = ps.x - pf.x, dy = ps.y - pf.y;
         const float d2 = dx * dx + dy * dy;
         const float inv = rsqrtf(d2);
@@ -450,6 +496,7 @@ __device__ __forceinline__ void contacts_via_smem(const PP &P, Scene<RT> &s, uin
         const float gS = pen * T.gS, gF = pen * T.gF;
         qs.x += gS * nx; qs.y += gS * ny;
         qf.x -= gF * nx; qf.y -= gF * ny;
+#endif
         q[F * pitch] = qf; q[S * pitch] = qs;
     } while (m);
     {
@@ -546,6 +593,21 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
         for (int r = 0; r < R; ++r) {
             float sn, cs;
             __sincosf(s.th[r], &sn, &cs);
+#ifndef RS_X_NOPACK_DRIVE
+            if constexpr (KIND == RS_KIND_VSS) {
+                // world -> robot frame, (v - a, v + a) of both components, robot -> world frame: 3 + 2 + 3
+                // instructions instead of 4 + 4 + 4
+                const float2 t = pk_mul(make_float2(s.vx[r], s.vy[r]), pk_bc(cs));
+                const float2 f = make_float2(fmaf(sn, s.vy[r], t.x), fmaf(-sn, s.vx[r], t.y));   // (vf, vl)
+                const float2 a = make_float2(P.acc_fwd_h, P.acc_lat_h);
+                const float2 hi = pk_add(f, a), lo = pk_sub(f, a);
+                const float vf = fmaxf(fminf(d.tf[r], hi.x), lo.x), vl = fmaxf(fminf(d.tl[r], hi.y), lo.y);
+                s.om[r] = fmaxf(fminf(d.tw[r], s.om[r] + P.acc_ang_h), s.om[r] - P.acc_ang_h);
+                const float2 u = pk_mul(make_float2(cs, sn), pk_bc(vf));
+                s.vx[r] = fmaf(-sn, vl, u.x); s.vy[r] = fmaf(cs, vl, u.y);
+                continue;
+            }
+#endif
             float vf = cs * s.vx[r] + sn * s.vy[r], vl = -sn * s.vx[r] + cs * s.vy[r];
             if constexpr (KIND == RS_KIND_VSS) {
                 // v + clamp(t - v, -a, a) == clamp(t, v - a, v + a): two independent adds, then min / max
@@ -578,10 +640,22 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
         // (d) integrate
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+#ifndef RS_X_NOPACK_INT
+            const float2 p = pk_fma(make_float2(s.vx[r], s.vy[r]), pk_bc(h), make_float2(s.x[r], s.y[r]));
+            s.x[r] = p.x; s.y[r] = p.y;
+#else
             s.x[r] += s.vx[r] * h; s.y[r] += s.vy[r] * h;
+#endif
             s.th[r] += s.om[r] * h;      // |omega| dt < 2 pi: wrapped once, after the last sub-step
         }
+#ifndef RS_X_NOPACK_INT
+        if (holder < 0) {
+            const float2 p = pk_fma(make_float2(s.bvx, s.bvy), pk_bc(h), make_float2(s.bx, s.by));
+            s.bx = p.x; s.by = p.y;
+        }
+#else
         if (holder < 0) { s.bx += s.bvx * h; s.by += s.bvy * h; }
+#endif
         else {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -616,13 +690,23 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
             for (int i = R - 2; i >= 0; --i) {
 #pragma unroll
                 for (int j = R - 1; j > i; --j) {
+#ifndef RS_X_NOPACK_MASK
+                    const float2 dd = pk_sub(make_float2(s.x[j], s.y[j]), make_float2(s.x[i], s.y[i]));
+                    const float dx = dd.x, dy = dd.y;
+#else
                     const float dx = s.x[j] - s.x[i], dy = s.y[j] - s.y[i];
+#endif
                     mrr = __funnelshift_l(__float_as_uint(fmaf(dx, dx, fmaf(dy, dy, -P.rs_rr2))), mrr, 1);
                 }
             }
 #pragma unroll
             for (int r = R - 1; r >= 0; --r) {
+#ifndef RS_X_NOPACK_MASK
+                const float2 dd = pk_sub(make_float2(s.bx, s.by), make_float2(s.x[r], s.y[r]));
+                const float dx = dd.x, dy = dd.y;
+#else
                 const float dx = s.bx - s.x[r], dy = s.by - s.y[r];
+#endif
                 mask = __funnelshift_l(__float_as_uint(fmaf(dx, dx, fmaf(dy, dy, -P.rs_br2))), mask, 1);
             }
             mask |= mrr << R;
