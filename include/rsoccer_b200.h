@@ -173,7 +173,8 @@ uint64_t rs_launch_count(const rs_world *w);
 /* which kernels step this world (diagnostics; the results do not depend on it):
  *   bit 0  task kernels run one lane per BODY (else one lane per MATCH)
  *   bit 1  rs_step runs one lane per BODY
- *   bit 2  physics constants are compile-time immediates (VSS, field_type 0, 25 ms) */
+ *   bit 2  physics constants are compile-time immediates (VSS, field_type 0, 25 ms)
+ *   bit 3  the VSS-v0 task kernel uses the packed fp32x2 instruction forms (large worlds; same results) */
 int rs_kernel_flags(const rs_world *w);
 
 #ifdef __cplusplus

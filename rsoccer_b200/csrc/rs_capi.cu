@@ -45,10 +45,12 @@ struct VssStepArgs {
 // VSSEnv.step for BS matches per CTA, one lane per match.  ONE launch = commands (agent +
 // OU noise), 5 physics sub-steps, reward/done/truncation, info accumulators, masked
 // auto-reset and the observation tile (leaves through a TMA bulk store).
-template <int NB, int NY, int BS, bool F0 /* physics constants are VssF0's: immediates instead of constant-bank loads */>
+template <int NB, int NY, int BS, int F0 /* 0: run-time physics constants.  1: VssF0's, immediates instead of
+          constant-bank loads.  2: VssF0P, the same with the packed fp32x2 instruction forms (rs_device.cuh) */>
 __global__ void __launch_bounds__(BS, RS_VSS_MINB(BS))
 k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
     constexpr int R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
+    constexpr bool PK = F0 == 2 && VssF0P::packed;
     // one region per WARP: its contact scratch during the physics (2 x (R + 1) rows of 32 float4
     // columns), then its 32 observation rows.  Nothing in it is ever touched by another warp.
     constexpr int SCRATCH = 2 * (R + 1) * 32 * 4, WF = 32 * NOBS > SCRATCH ? 32 * NOBS : SCRATCH;
@@ -116,26 +118,28 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         Drive<R> d;
         d.drib = 0;
         float wl0, wr0;
-        vss_action_to_wheels(P, act.x, act.y, wl0, wr0);
-        vss_target(P, wl0, wr0, d.tf[0], d.tw[0]);
+        vss_action_to_wheels<PK>(P, act.x, act.y, wl0, wr0);
+        vss_target<PK>(P, wl0, wr0, d.tf[0], d.tw[0]);
         d.tl[0] = 0.0f; d.kick[0] = 0.0f;
         if (A.cmds_out) { A.cmds_out[(size_t)e * R * 2] = wl0; A.cmds_out[(size_t)e * R * 2 + 1] = wr0; }
 #pragma unroll
         for (int r = 1; r < R; ++r) {
             // Utils/Utils.py:14-21 OU sample (mu = 0, sigma = 0.5, theta = 0.17)
             float2 o = ou[r - 1];
-            o.x = o.x + (float)RS_OU_THETA * (0.0f - o.x) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z[2 * (r - 1)];
-            o.y = o.y + (float)RS_OU_THETA * (0.0f - o.y) * P.dt + (float)RS_OU_SIGMA * P.sqrt_dt * z[2 * (r - 1) + 1];
+            // x + theta (0 - x) dt + sigma sqrt(dt) z for both wheels at once
+            o = v_fma<PK>(o, bc2(-(float)RS_OU_THETA * P.dt), o);
+            o = v_fma<PK>(make_float2(z[2 * (r - 1)], z[2 * (r - 1) + 1]), bc2((float)RS_OU_SIGMA * P.sqrt_dt), o);
             S.ou[(size_t)(r - 1) * S.np + e] = o;
             float wl, wr;
-            vss_action_to_wheels(P, o.x, o.y, wl, wr);
-            vss_target(P, wl, wr, d.tf[r], d.tw[r]);
+            vss_action_to_wheels<PK>(P, o.x, o.y, wl, wr);
+            vss_target<PK>(P, wl, wr, d.tf[r], d.tw[r]);
             d.tl[r] = 0.0f; d.kick[r] = 0.0f;
             if (A.cmds_out) { A.cmds_out[((size_t)e * R + r) * 2] = wl; A.cmds_out[((size_t)e * R + r) * 2 + 1] = wr; }
         }
 
         // ---- rsim.send_commands + get_frame, vss_gym_base.py:77-82
-        if constexpr (F0) physics_step<RS_KIND_VSS, R>(VssF0{}, s, d, live, cq, cp0, 32);
+        if constexpr (F0 == 2) physics_step<RS_KIND_VSS, R>(VssF0P{}, s, d, live, cq, cp0, 32);
+        else if constexpr (F0 == 1) physics_step<RS_KIND_VSS, R>(VssF0{}, s, d, live, cq, cp0, 32);
         else physics_step<RS_KIND_VSS, R>(P, s, d, live, cq, cp0, 32);
 
         // ---- the task words (loaded at the top) are first needed here, after the physics
@@ -196,7 +200,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         S.steps[e] = steps | ((has_prev ? 1 : 0) << 24);
         S.prev[e] = prev;
         __syncwarp(live);      // the rows below overlay the other lanes' contact scratch
-        vss_obs<NB, NY>(P, s, wtile + (tid & 31) * NOBS);
+        vss_obs<NB, NY, PK>(P, s, wtile + (tid & 31) * NOBS);
         step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
     }
     // the rows of a warp are one contiguous span of global memory: every lane of the warp (live
@@ -1006,6 +1010,7 @@ struct rs_world {
     int block;               // CTA size of the step kernels
     int per_match;           // 1: one lane per MATCH kernels (rs_device.cuh); 0: one lane per BODY (rs_lanes.cuh); -1: by world size
     int lane_block;          // CTA size of the lane-per-body kernels
+    int packed;              // 1: packed fp32x2 instruction forms in the VssF0 kernels; 0: scalar forms; -1: by world size
     // scratch for the *_host entry points (library owned)
     float *s_actions, *s_obs, *s_reward;
     uint8_t *s_done, *s_trunc;
@@ -1102,6 +1107,19 @@ static bool use_lane_per_body(const rs_world *w, bool task_kernel) {
     return task_kernel ? w->n < 14000 : true;
 }
 
+// Packed fp32x2 forms (VssF0P, rs_device.cuh) or scalar forms in the VssF0 lane-per-match kernels?  Same
+// results bit for bit (tests/test_gpu_api.py); fewer issued instructions but longer dependent
+// chains, so it is a matter of world size: 16 384 matches 8.21 (scalar) vs 8.30 us (packed), 24 576
+// matches 9.90 vs 9.50 us, 65 536 matches 17.05 vs 15.71 us (profiles/r1d_packed.txt).  The whole world decides, not
+// the chunk a launch covers.
+#ifndef RS_PACKED_MIN_MATCHES
+#define RS_PACKED_MIN_MATCHES 20480
+#endif
+static bool use_packed(const rs_world *w) {
+    if (w->packed >= 0) return w->packed != 0;
+    return w->n >= RS_PACKED_MIN_MATCHES;
+}
+
 // Launch of a step kernel, by default with programmatic stream serialization (PDL): the
 // kernel's pre-wait part overlaps the tail of its predecessor in the stream (rs_device.cuh).
 static bool g_pdl = true;
@@ -1182,6 +1200,8 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     w->block = 64;
     w->per_match = -1; w->lane_block = 128;
     if (const char *ls = getenv("RS_PER_MATCH")) w->per_match = atoi(ls) != 0;
+    w->packed = -1;
+    if (const char *ls = getenv("RS_PACKED")) w->packed = atoi(ls) != 0;
     if (const char *ls = getenv("RS_PDL")) g_pdl = atoi(ls) != 0;
     if (const char *bs = getenv("RS_LANE_BLOCK")) { const int b = atoi(bs); if (b == 64 || b == 128 || b == 256) w->lane_block = b; }
     w->f0 = matches_vss_f0(w->dp) ? 1 : 0;
@@ -1316,7 +1336,8 @@ uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches : 0; }
 
 int rs_kernel_flags(const rs_world *w) {
     if (!w) return 0;
-    return (use_lane_per_body(w, true) ? 1 : 0) | (use_lane_per_body(w, false) ? 2 : 0) | (w->f0 ? 4 : 0);
+    return (use_lane_per_body(w, true) ? 1 : 0) | (use_lane_per_body(w, false) ? 2 : 0) | (w->f0 ? 4 : 0) |
+           (w->f0 && !use_lane_per_body(w, true) && use_packed(w) ? 8 : 0);
 }
 
 static void push_t(rs_world *w, cudaStream_t st) {
@@ -1380,12 +1401,14 @@ static void launch_vss(rs_world *w, const VssStepArgs &A, const StatePtrs &S, cu
         if (w->lane_block == 256) launch_step_kernel(k_vss_env_step_lanes<256>, (n + 31) / 32, 256, st, w->dp, S, A);
         else if (w->lane_block == 64) launch_step_kernel(k_vss_env_step_lanes<64>, (n + 7) / 8, 64, st, w->dp, S, A);
         else launch_step_kernel(k_vss_env_step_lanes<128>, (n + 15) / 16, 128, st, w->dp, S, A);
-    } else if (w->f0) switch (w->block) {
-        case 32: launch_step_kernel(k_vss_env_step<3, 3, 32, true>, (n + 31) / 32, 32, st, w->dp, S, A); break;
-        case 128: launch_step_kernel(k_vss_env_step<3, 3, 128, true>, (n + 127) / 128, 128, st, w->dp, S, A); break;
-        default: launch_step_kernel(k_vss_env_step<3, 3, 64, true>, (n + 63) / 64, 64, st, w->dp, S, A); break;
+    } else if (w->f0 && use_packed(w)) switch (w->block) {
+        case 32: launch_step_kernel(k_vss_env_step<3, 3, 32, 2>, (n + 31) / 32, 32, st, w->dp, S, A); break;
+        case 128: launch_step_kernel(k_vss_env_step<3, 3, 128, 2>, (n + 127) / 128, 128, st, w->dp, S, A); break;
+        default: launch_step_kernel(k_vss_env_step<3, 3, 64, 2>, (n + 63) / 64, 64, st, w->dp, S, A); break;
+    } else if (w->f0) {
+        launch_step_kernel(k_vss_env_step<3, 3, 64, 1>, (n + 63) / 64, 64, st, w->dp, S, A);
     } else {
-        launch_step_kernel(k_vss_env_step<3, 3, 64, false>, (n + 63) / 64, 64, st, w->dp, S, A);
+        launch_step_kernel(k_vss_env_step<3, 3, 64, 0>, (n + 63) / 64, 64, st, w->dp, S, A);
     }
     w->launches++;
 }

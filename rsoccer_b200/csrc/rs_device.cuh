@@ -24,6 +24,7 @@
 #define RS_DEG_F 57.29577951308232f
 
 struct DevParams {
+    static constexpr bool packed = false;   // see v_sub / v_mul / v_fma below
     int kind, n_blue, n_yellow, n_robots;
     float dt, h;
     // field
@@ -53,6 +54,7 @@ struct DevParams {
 // sees immediates instead of constant-bank loads.  rs_capi.cu checks it field by field against
 // the run-time block before it selects a kernel built on it.
 struct VssF0 {
+    static constexpr bool packed = false;
     static constexpr double h_ = 0.025 / RS_SUBSTEPS, wb_ = 1.0 / 0.046, wr_ = 1.0 / 0.18;
     static constexpr double br_ = 0.0375 + 0.0215, rr_ = 2.0 * 0.0375;
     static constexpr int n_robots = 6;
@@ -67,6 +69,13 @@ struct VssF0 {
     static constexpr float ball_decel_h = (float)(0.05 * 9.81 * h_);
     static constexpr float rs_br = (float)br_, rs_br2 = (float)(br_ * br_), rs_rr = (float)rr_, rs_rr2 = (float)(rr_ * rr_);
     static constexpr float acc_fwd_h = (float)(6.0 * h_), acc_lat_h = (float)(9.0 * h_), acc_ang_h = (float)(200.0 * h_);
+};
+// VssF0 with the packed fp32x2 instruction forms (below): the kernels of worlds large enough to be
+// bound by issue slots; RS_X_NOPACK = tuning knob, the scalar forms everywhere
+struct VssF0P : VssF0 {
+#ifndef RS_X_NOPACK
+    static constexpr bool packed = true;
+#endif
 };
 __device__ __forceinline__ float wall_lx(const DevParams &P) { return P.box[0][0]; }
 __device__ __forceinline__ float wall_ly(const DevParams &P) { return P.box[0][1]; }
@@ -94,10 +103,16 @@ struct Drive {
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 // Packed fp32x2 arithmetic of sm_100 (SASS FFMA2 / FADD2 / FMUL2; a scalar register or an
 // immediate broadcasts into both halves, negation is an operand modifier): two IEEE results per
-// issued instruction, each half rounded exactly like the scalar instruction.  The step kernels
-// are bound by issue slots and dependent latency, not by the FMA pipe, so every
-// (x, y) / (vx, vy) operation of a body -- the halves of the register quad its state was loaded
-// into -- is issued as one instruction.  RS_X_NOPACK* = scalar form (tuning knobs).
+// issued instruction, each half rounded exactly like the scalar instruction.  Every (x, y) /
+// (vx, vy) operation of a body -- the halves of the register quad its state was loaded into --
+// can be issued as one instruction.  It pays where a kernel is bound by issue slots (VSS-v0,
+// one lane per match, >= ~20 000 matches: 16.65 -> 15.7 us at 65 536) and costs where it is
+// bound by the dependent latency of a few warps (the packed forms are slower to return: VSS-v0
+// at 4 096 matches 7.24 -> 7.54 us, SSL 1 v 1 at 16 384 7.15 -> 7.27 us), so the source is
+// written once on float2 and the parameter class picks the instruction form (PP::packed).
+__device__ __forceinline__ float2 pk_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 pk_fma(const float2 a, const float2 b, const float2 c) { return __ffma2_rn(a, b, c); }
 // a - b as ONE instruction: written as add(a, -b) the compiler keeps a negated copy of every body that enters
 // several pairs (two FADD each) instead of using the operand modifier
 __device__ __forceinline__ float2 pk_sub(const float2 a, const float2 b) {
@@ -107,10 +122,19 @@ __device__ __forceinline__ float2 pk_sub(const float2 a, const float2 b) {
         : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return r;
 }
-__device__ __forceinline__ float2 pk_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 pk_fma(const float2 a, const float2 b, const float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 pk_bc(const float a) { return make_float2(a, a); }
+template <bool PK> __device__ __forceinline__ float2 v_add(const float2 a, const float2 b) {
+    if constexpr (PK) return pk_add(a, b); else return make_float2(a.x + b.x, a.y + b.y);
+}
+template <bool PK> __device__ __forceinline__ float2 v_sub(const float2 a, const float2 b) {
+    if constexpr (PK) return pk_sub(a, b); else return make_float2(a.x - b.x, a.y - b.y);
+}
+template <bool PK> __device__ __forceinline__ float2 v_mul(const float2 a, const float2 b) {
+    if constexpr (PK) return pk_mul(a, b); else return make_float2(a.x * b.x, a.y * b.y);
+}
+template <bool PK> __device__ __forceinline__ float2 v_fma(const float2 a, const float2 b, const float2 c) {
+    if constexpr (PK) return pk_fma(a, b, c); else return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+}
+__device__ __forceinline__ float2 bc2(const float a) { return make_float2(a, a); }
 __device__ __forceinline__ float wrap_pi(float a) {
     if (a > RS_PI_F) a -= 2.0f * RS_PI_F; else if (a <= -RS_PI_F) a += 2.0f * RS_PI_F;
     return a;
@@ -127,7 +151,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// ((x >> 8) + 0.5) / 2^24 as one FMA: scaling by a power of two commutes with rounding, so this is bit for
+// bit the add-then-multiply form the oracle uses
+__device__ __forceinline__ float u01(uint32_t x) { return fmaf((float)(x >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f); }
 
 struct Rng {   // sequential u32 stream for (env, t, stream): counter (env, t, stream, j)
     uint4 ctr; uint2 key; uint4 buf; int idx;
@@ -265,12 +291,8 @@ __device__ __forceinline__ void vss_walls(const PP &P, const float r, const floa
             if (dy < dx) xlim = XO; else ylim = YO;
         }
     }
-#ifndef RS_X_NOPACK_WALL
-    const float2 oo = pk_mul(make_float2(vx, vy), make_float2(x, y));
+    const float2 oo = v_mul<PP::packed>(make_float2(vx, vy), make_float2(x, y));
     const float ox = oo.x, oy = oo.y;                     // > 0: moving outward
-#else
-    const float ox = vx * x, oy = vy * y;                 // > 0: moving outward
-#endif
     const bool hx = fabsf(x) > xlim, hy = fabsf(y) > ylim;
     x = fmaxf(fminf(x, xlim), -xlim); y = fmaxf(fminf(y, ylim), -ylim);
     if (hx && ox > 0.0f) vx = wall_bounce(P, e, vx);
@@ -425,11 +447,41 @@ __device__ __forceinline__ ContactTab<PP> contact_tab(const PP &P, const bool ba
     t.gS = ball ? P.fb : 0.5f; t.gF = ball ? P.fr : 0.5f;
     return t;
 }
+// The same per pair, for the compile-time world (VssF0), as a table indexed by the pair number: body
+// indices and the eight constants of the pair's type arrive with three 16-byte loads instead of
+// a bit-table decode and a chain of selects (~30 instructions per resolved contact; 2-3 lanes of
+// a warp are active here, each reading the entry of its own pair).
+struct alignas(16) PairEnt { int F, S; float rs, rc, kn, wS, wF, mu, gS, gF, inv_wsum, pad; };
+template <int RT> struct PairTab { PairEnt e[RT + RT * (RT - 1) / 2]; };
+template <int RT> constexpr PairTab<RT> make_pair_tab_f0() {
+    PairTab<RT> t{};
+    for (int p = 0; p < RT + RT * (RT - 1) / 2; ++p) {
+        const bool ball = p < RT;
+        PairEnt &e = t.e[p];
+        e.F = ball ? p + 1 : 1 + rr_pair_i<RT>(p - RT);
+        e.S = ball ? 0 : 1 + rr_pair_j<RT>(p - RT);
+        e.rs = ball ? VssF0::rs_br : VssF0::rs_rr;
+        e.rc = ball ? VssF0::rbt_r : 0.0f;
+        e.kn = ball ? (1.0f + VssF0::e_ball_rbt) * VssF0::inv_wsum : (1.0f + VssF0::e_rbt_rbt) * 0.5f;
+        e.wS = ball ? VssF0::wb : 1.0f; e.wF = ball ? VssF0::wr : 1.0f;
+        e.mu = ball ? VssF0::mu_ball_rbt : 0.0f;
+        e.gS = ball ? VssF0::fb : 0.5f; e.gF = ball ? VssF0::fr : 0.5f;
+        e.inv_wsum = VssF0::inv_wsum; e.pad = 0.0f;
+    }
+    return t;
+}
+// In global memory, read through the read-only path (LDG.CONSTANT, L1-resident after the first touch), NOT
+// in __constant__ memory: a user constant bank in the module added 0.1-0.3 us to EVERY kernel
+// launch of the library (7.27 -> 7.57 us for the 4 096-match VSS-v0 step, which never reads the
+// table; gpurun_out/run39.log), far more than the table saves.
+template <int RT> __device__ const PairTab<RT> g_pair_tab_f0 = make_pair_tab_f0<RT>();
+
 template <int RT, class PP>
 __device__ __forceinline__ void contacts_via_smem(const PP &P, Scene<RT> &s, uint32_t m, float4 *q, float4 *p0, const int pitch) {
     static_assert(RT >= 1 && RT <= 7, "3-bit body indices, 21 robot pairs in 63 bits");
     // q[b] straight from the register quads of the scene; the phase-start copy as (x, y) pairs and
     // the angular velocities as scalars (no register shuffling to build (x, y, omega, -) quads)
+    constexpr bool PK = PP::packed;
     const int lane = threadIdx.x & 31;               // q / p0 point at this lane's float4 column of its warp's region
     float2 *const pxy = reinterpret_cast<float2 *>(p0 - lane) + lane;
     float *const pom = reinterpret_cast<float *>(p0 - lane + (RT + 1) * pitch / 2) + lane;
@@ -445,58 +497,45 @@ __device__ __forceinline__ void contacts_via_smem(const PP &P, Scene<RT> &s, uin
         const int p = __ffs((int)m) - 1;
         m &= m - 1;
         // normal points F -> S.  ball pairs: F = robot p, S = ball (body 0)
-        const bool ball = p < RT;
-        const int k3 = 3 * (p - RT);
-        const int F = ball ? p + 1 : 1 + (int)((TI >> k3) & 7u), S = ball ? 0 : 1 + (int)((TJ >> k3) & 7u);
-        const ContactTab<PP> T = contact_tab(P, ball);
+        int F, S;
+        ContactTab<PP> T;
+#ifndef RS_X_NOPAIRTAB
+        if constexpr (PP::packed) {                      // VssF0P
+            const float4 *const e = reinterpret_cast<const float4 *>(&g_pair_tab_f0<RT>.e[p]);
+            const float4 e0 = __ldg(e), e1 = __ldg(e + 1), e2 = __ldg(e + 2);
+            F = __float_as_int(e0.x); S = __float_as_int(e0.y);
+            T.rs = e0.z; T.rc = e0.w; T.kn = e1.x; T.wS = e1.y; T.wF = e1.z; T.mu = e1.w; T.gS = e2.x; T.gF = e2.y;
+        } else
+#endif
+        {
+            const bool ball = p < RT;
+            const int k3 = 3 * (p - RT);
+            F = ball ? p + 1 : 1 + (int)((TI >> k3) & 7u); S = ball ? 0 : 1 + (int)((TJ >> k3) & 7u);
+            T = contact_tab(P, ball);
+        }
         const float2 pf = pxy[F * pitch], ps = pxy[S * pitch];
         const float omf = pom[F * pitch];
         float4 qf = q[F * pitch], qs = q[S * pitch];
-#ifndef RS_X_NOPACK_CONTACT
-        const float2 dd = pk_sub(ps, pf);
+        const float2 dd = v_sub<PK>(ps, pf);
         const float d2 = dd.x * dd.x + dd.y * dd.y;
         const float inv = rsqrtf(d2);
         const bool ok = d2 > 1e-12f;
-        float2 n = pk_mul(dd, pk_bc(inv));
+        float2 n = v_mul<PK>(dd, bc2(inv));
         n.x = ok ? n.x : 1.0f; n.y = ok ? n.y : 0.0f;
         const float d = ok ? d2 * inv : 0.0f;
         const float pen = T.rs - d;
-        const float2 rc = pk_mul(n, pk_bc(T.rc));
-        const float2 rel = pk_sub(make_float2(qs.z, qs.w), make_float2(qf.z - omf * rc.y, qf.w + omf * rc.x));   // S - F's surface velocity
+        const float2 rc = v_mul<PK>(n, bc2(T.rc));
+        const float2 rel = v_sub<PK>(make_float2(qs.z, qs.w), make_float2(qf.z - omf * rc.y, qf.w + omf * rc.x));   // S - F's surface velocity
         const float vn = fminf(rel.x * n.x + rel.y * n.y, 0.0f);       // separating: every impulse below is +-0
         // ball pair: Jn = -(1 + e) vn / (wb + wr), dv = Jn w n.  robot pair: equal masses, dv = -(1 + e) vn / 2 n
         const float Jn = -T.kn * vn;
         const float vt = rel.y * n.x - rel.x * n.y;                    // tangent (-ny, nx)
         const float Jt = clampf(-vt * P.inv_wsum, -T.mu * Jn, T.mu * Jn);
-        float2 vs = pk_fma(n, pk_bc(Jn * T.wS), make_float2(qs.z, qs.w)), vf = pk_fma(n, pk_bc(-Jn * T.wF), make_float2(qf.z, qf.w));
+        float2 vs = v_fma<PK>(n, bc2(Jn * T.wS), make_float2(qs.z, qs.w)), vf = v_fma<PK>(n, bc2(-Jn * T.wF), make_float2(qf.z, qf.w));
         const float jS = Jt * T.wS, jF = Jt * T.wF;
         vs.x -= jS * n.y; vs.y += jS * n.x; vf.x += jF * n.y; vf.y -= jF * n.x;
-        const float2 xs = pk_fma(n, pk_bc(pen * T.gS), make_float2(qs.x, qs.y)), xf = pk_fma(n, pk_bc(-pen * T.gF), make_float2(qf.x, qf.y));
+        const float2 xs = v_fma<PK>(n, bc2(pen * T.gS), make_float2(qs.x, qs.y)), xf = v_fma<PK>(n, bc2(-pen * T.gF), make_float2(qf.x, qf.y));
         qs = make_float4(xs.x, xs.y, vs.x, vs.y); qf = make_float4(xf.x, xf.y, vf.x, vf.y);
-#else
-        const float dx = ps.x - pf.x, dy = ps.y - pf.y;
-        const float d2 = dx * dx + dy * dy;
-        const float inv = rsqrtf(d2);
-        const bool ok = d2 > 1e-12f;
-        const float nx = ok ? dx * inv : 1.0f, ny = ok ? dy * inv : 0.0f, d = ok ? d2 * inv : 0.0f;
-        const float pen = T.rs - d;
-        const float rcx = nx * T.rc, rcy = ny * T.rc;
-        const float sx = qf.z - omf * rcy, sy = qf.w + omf * rcx;     // F's surface velocity at the contact
-        const float relx = qs.z - sx, rely = qs.w - sy;
-        const float vn = fminf(relx * nx + rely * ny, 0.0f);          // separating: every impulse below is +-0
-        // ball pair: Jn = -(1 + e) vn / (wb + wr), dv = Jn w n.  robot pair: equal masses, dv = -(1 + e) vn / 2 n
-        const float Jn = -T.kn * vn;
-        qs.z += Jn * T.wS * nx; qs.w += Jn * T.wS * ny;
-        qf.z -= Jn * T.wF * nx; qf.w -= Jn * T.wF * ny;
-        const float tx = -ny, ty = nx;
-        const float vt = relx * tx + rely * ty;
-        const float Jt = clampf(-vt * P.inv_wsum, -T.mu * Jn, T.mu * Jn);
-        qs.z += Jt * T.wS * tx; qs.w += Jt * T.wS * ty;
-        qf.z -= Jt * T.wF * tx; qf.w -= Jt * T.wF * ty;
-        const float gS = pen * T.gS, gF = pen * T.gF;
-        qs.x += gS * nx; qs.y += gS * ny;
-        qf.x -= gF * nx; qf.y -= gF * ny;
-#endif
         q[F * pitch] = qf; q[S * pitch] = qs;
     } while (m);
     {
@@ -538,10 +577,11 @@ __device__ __forceinline__ void contacts_static(const PP &P, Scene<RT> &s, const
 }
 
 // commands -> drive targets.  VSS: cmd = (wl, wr) rad/s (rsim.py:100-101)
+template <bool PK = false>
 __device__ __forceinline__ void vss_target(const DevParams &P, float wl, float wr, float &tf, float &tw) {
     wl = clampf(wl, -P.wmax, P.wmax); wr = clampf(wr, -P.wmax, P.wmax);
-    tf = P.rw * (wl + wr) * 0.5f;
-    tw = P.rw * (wr - wl) * P.inv_2b;
+    const float2 t = v_mul<PK>(make_float2(wl + wr, wr - wl), make_float2(P.rw * 0.5f, P.rw * P.inv_2b));
+    tf = t.x; tw = t.y;
 }
 // SSL: cmd = 8 floats (rsim.py:137-153)
 __device__ __forceinline__ void ssl_target(const DevParams &P, const float (&cmd)[8], float &tf,
@@ -567,6 +607,7 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
                                              const unsigned live /* lanes of this warp that call */,
                                              float4 *cq = nullptr /* this lane's column of the contact scratch */,
                                              float4 *cp0 = nullptr, const int cpitch = 0) {
+    constexpr bool PK = PP::packed;
     const int R = RT > 0 ? RT : P.n_robots;
     const float h = P.h;
     uint32_t kicked = 0;
@@ -593,26 +634,14 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
         for (int r = 0; r < R; ++r) {
             float sn, cs;
             __sincosf(s.th[r], &sn, &cs);
-#ifndef RS_X_NOPACK_DRIVE
+            // world -> robot frame on the (vx, vy) pair
+            const float2 t = v_mul<PK>(make_float2(s.vx[r], s.vy[r]), bc2(cs));
+            float vf = fmaf(sn, s.vy[r], t.x), vl = fmaf(-sn, s.vx[r], t.y);
             if constexpr (KIND == RS_KIND_VSS) {
-                // world -> robot frame, (v - a, v + a) of both components, robot -> world frame: 3 + 2 + 3
-                // instructions instead of 4 + 4 + 4
-                const float2 t = pk_mul(make_float2(s.vx[r], s.vy[r]), pk_bc(cs));
-                const float2 f = make_float2(fmaf(sn, s.vy[r], t.x), fmaf(-sn, s.vx[r], t.y));   // (vf, vl)
-                const float2 a = make_float2(P.acc_fwd_h, P.acc_lat_h);
-                const float2 hi = pk_add(f, a), lo = pk_sub(f, a);
-                const float vf = fmaxf(fminf(d.tf[r], hi.x), lo.x), vl = fmaxf(fminf(d.tl[r], hi.y), lo.y);
-                s.om[r] = fmaxf(fminf(d.tw[r], s.om[r] + P.acc_ang_h), s.om[r] - P.acc_ang_h);
-                const float2 u = pk_mul(make_float2(cs, sn), pk_bc(vf));
-                s.vx[r] = fmaf(-sn, vl, u.x); s.vy[r] = fmaf(cs, vl, u.y);
-                continue;
-            }
-#endif
-            float vf = cs * s.vx[r] + sn * s.vy[r], vl = -sn * s.vx[r] + cs * s.vy[r];
-            if constexpr (KIND == RS_KIND_VSS) {
-                // v + clamp(t - v, -a, a) == clamp(t, v - a, v + a): two independent adds, then min / max
-                vf = fmaxf(fminf(d.tf[r], vf + P.acc_fwd_h), vf - P.acc_fwd_h);
-                vl = fmaxf(fminf(d.tl[r], vl + P.acc_lat_h), vl - P.acc_lat_h);
+                // v + clamp(t - v, -a, a) == clamp(t, v - a, v + a): independent adds, then min / max
+                const float2 f = make_float2(vf, vl), a = make_float2(P.acc_fwd_h, P.acc_lat_h);
+                const float2 hi = v_add<PK>(f, a), lo = v_sub<PK>(f, a);
+                vf = fmaxf(fminf(d.tf[r], hi.x), lo.x); vl = fmaxf(fminf(d.tl[r], hi.y), lo.y);
             } else {
                 const float df = d.tf[r] - vf, dl = d.tl[r] - vl;
                 const float n2 = df * df + dl * dl;
@@ -621,7 +650,8 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
                 vf += df * sc; vl += dl * sc;
             }
             s.om[r] = fmaxf(fminf(d.tw[r], s.om[r] + P.acc_ang_h), s.om[r] - P.acc_ang_h);
-            s.vx[r] = cs * vf - sn * vl; s.vy[r] = sn * vf + cs * vl;
+            const float2 u = v_mul<PK>(make_float2(cs, sn), bc2(vf));        // robot -> world frame
+            s.vx[r] = fmaf(-sn, vl, u.x); s.vy[r] = fmaf(cs, vl, u.y);
             if constexpr (KIND == RS_KIND_SSL) {
                 if (holder < 0 && ((d.drib >> r) & 1u) && !((kicked >> r) & 1u)) {
                     const float dx = s.bx - s.x[r], dy = s.by - s.y[r];
@@ -635,27 +665,20 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
         if (holder < 0) {
             const float sp2 = s.bvx * s.bvx + s.bvy * s.bvy;
             const float sc = fmaxf(1.0f - P.ball_decel_h * rsqrtf(sp2 + 1e-12f), 0.0f);
-            s.bvx *= sc; s.bvy *= sc;
+            const float2 bv = v_mul<PK>(make_float2(s.bvx, s.bvy), bc2(sc));
+            s.bvx = bv.x; s.bvy = bv.y;
         }
         // (d) integrate
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-#ifndef RS_X_NOPACK_INT
-            const float2 p = pk_fma(make_float2(s.vx[r], s.vy[r]), pk_bc(h), make_float2(s.x[r], s.y[r]));
+            const float2 p = v_fma<PK>(make_float2(s.vx[r], s.vy[r]), bc2(h), make_float2(s.x[r], s.y[r]));
             s.x[r] = p.x; s.y[r] = p.y;
-#else
-            s.x[r] += s.vx[r] * h; s.y[r] += s.vy[r] * h;
-#endif
             s.th[r] += s.om[r] * h;      // |omega| dt < 2 pi: wrapped once, after the last sub-step
         }
-#ifndef RS_X_NOPACK_INT
         if (holder < 0) {
-            const float2 p = pk_fma(make_float2(s.bvx, s.bvy), pk_bc(h), make_float2(s.bx, s.by));
+            const float2 p = v_fma<PK>(make_float2(s.bvx, s.bvy), bc2(h), make_float2(s.bx, s.by));
             s.bx = p.x; s.by = p.y;
         }
-#else
-        if (holder < 0) { s.bx += s.bvx * h; s.by += s.bvy * h; }
-#endif
         else {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -690,23 +713,15 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
             for (int i = R - 2; i >= 0; --i) {
 #pragma unroll
                 for (int j = R - 1; j > i; --j) {
-#ifndef RS_X_NOPACK_MASK
-                    const float2 dd = pk_sub(make_float2(s.x[j], s.y[j]), make_float2(s.x[i], s.y[i]));
+                    const float2 dd = v_sub<PK>(make_float2(s.x[j], s.y[j]), make_float2(s.x[i], s.y[i]));
                     const float dx = dd.x, dy = dd.y;
-#else
-                    const float dx = s.x[j] - s.x[i], dy = s.y[j] - s.y[i];
-#endif
                     mrr = __funnelshift_l(__float_as_uint(fmaf(dx, dx, fmaf(dy, dy, -P.rs_rr2))), mrr, 1);
                 }
             }
 #pragma unroll
             for (int r = R - 1; r >= 0; --r) {
-#ifndef RS_X_NOPACK_MASK
-                const float2 dd = pk_sub(make_float2(s.bx, s.by), make_float2(s.x[r], s.y[r]));
+                const float2 dd = v_sub<PK>(make_float2(s.bx, s.by), make_float2(s.x[r], s.y[r]));
                 const float dx = dd.x, dy = dd.y;
-#else
-                const float dx = s.bx - s.x[r], dy = s.by - s.y[r];
-#endif
                 mask = __funnelshift_l(__float_as_uint(fmaf(dx, dx, fmaf(dy, dy, -P.rs_br2))), mask, 1);
             }
             mask |= mrr << R;

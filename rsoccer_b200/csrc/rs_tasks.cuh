@@ -7,40 +7,51 @@
 #include "rs_device.cuh"
 
 // vss_gym.py:235-254 _actions_to_v_wheels: action in [-1,1] -> wheel rad/s, clip, 0.05 m/s deadzone
+template <bool PK = false>
 __device__ __forceinline__ void vss_action_to_wheels(const DevParams &P, float a0, float a1,
                                                      float &wl, float &wr) {
-    float l = clampf(a0 * P.max_v, -P.max_v, P.max_v), r = clampf(a1 * P.max_v, -P.max_v, P.max_v);
-    if (-(float)RS_VSS_DEADZONE < l && l < (float)RS_VSS_DEADZONE) l = 0.0f;
-    if (-(float)RS_VSS_DEADZONE < r && r < (float)RS_VSS_DEADZONE) r = 0.0f;
-    wl = l * P.inv_rw; wr = r * P.inv_rw;
+    const float2 v = v_mul<PK>(make_float2(a0, a1), bc2(P.max_v));
+    float l = clampf(v.x, -P.max_v, P.max_v), r = clampf(v.y, -P.max_v, P.max_v);
+    if (fabsf(l) < (float)RS_VSS_DEADZONE) l = 0.0f;      // -dz < l < dz
+    if (fabsf(r) < (float)RS_VSS_DEADZONE) r = 0.0f;
+    const float2 w = v_mul<PK>(make_float2(l, r), bc2(P.inv_rw));
+    wl = w.x; wr = w.y;
 }
 
 __device__ __forceinline__ float nrm(float v, float inv) {
     return clampf(v * inv, -(float)RS_NORM_BOUNDS, (float)RS_NORM_BOUNDS);
 }
 
+// two components with one scale, then the clamps
+template <bool PK>
+__device__ __forceinline__ void nrm2(const float a, const float b, const float inv, float &oa, float &ob) {
+    const float2 t = v_mul<PK>(make_float2(a, b), bc2(inv));
+    oa = clampf(t.x, -(float)RS_NORM_BOUNDS, (float)RS_NORM_BOUNDS); ob = clampf(t.y, -(float)RS_NORM_BOUNDS, (float)RS_NORM_BOUNDS);
+}
+
 // vss_gym.py:93-117 _frame_to_observations; o = row of 4 + 7 NB + 5 NY floats
-template <int NB, int NY>
+template <int NB, int NY, bool PK = false>
 __device__ __forceinline__ void vss_obs(const DevParams &P, const Scene<NB + NY> &s, float *o) {
     constexpr int NOBS = 4 + 7 * NB + 5 * NY;
     float v[NOBS];
     int k = 0;
-    v[k++] = nrm(s.bx, P.inv_max_pos); v[k++] = nrm(s.by, P.inv_max_pos);
-    v[k++] = nrm(s.bvx, P.inv_max_v); v[k++] = nrm(s.bvy, P.inv_max_v);
+    nrm2<PK>(s.bx, s.by, P.inv_max_pos, v[k], v[k + 1]); nrm2<PK>(s.bvx, s.bvy, P.inv_max_v, v[k + 2], v[k + 3]); k += 4;
 #pragma unroll
     for (int r = 0; r < NB; ++r) {
         float sn, cs;
         __sincosf(s.th[r], &sn, &cs);
-        v[k++] = nrm(s.x[r], P.inv_max_pos); v[k++] = nrm(s.y[r], P.inv_max_pos);
-        v[k++] = sn; v[k++] = cs;
-        v[k++] = nrm(s.vx[r], P.inv_max_v); v[k++] = nrm(s.vy[r], P.inv_max_v);
-        v[k++] = nrm(s.om[r], P.inv_max_w_rad);
+        nrm2<PK>(s.x[r], s.y[r], P.inv_max_pos, v[k], v[k + 1]);
+        v[k + 2] = sn; v[k + 3] = cs;
+        nrm2<PK>(s.vx[r], s.vy[r], P.inv_max_v, v[k + 4], v[k + 5]);
+        v[k + 6] = nrm(s.om[r], P.inv_max_w_rad);
+        k += 7;
     }
 #pragma unroll
     for (int r = NB; r < NB + NY; ++r) {
-        v[k++] = nrm(s.x[r], P.inv_max_pos); v[k++] = nrm(s.y[r], P.inv_max_pos);
-        v[k++] = nrm(s.vx[r], P.inv_max_v); v[k++] = nrm(s.vy[r], P.inv_max_v);
-        v[k++] = nrm(s.om[r], P.inv_max_w_rad);
+        nrm2<PK>(s.x[r], s.y[r], P.inv_max_pos, v[k], v[k + 1]);
+        nrm2<PK>(s.vx[r], s.vy[r], P.inv_max_v, v[k + 2], v[k + 3]);
+        v[k + 4] = nrm(s.om[r], P.inv_max_w_rad);
+        k += 5;
     }
     if ((NOBS & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0u)) {
         float4 *o4 = reinterpret_cast<float4 *>(o);

@@ -238,6 +238,33 @@ def test_preset_kernel_is_selected_and_matches_the_generic_one(engine, monkeypat
     assert bad <= 4, bad
 
 
+def test_packed_and_scalar_instruction_forms_agree_bit_for_bit(engine, monkeypatch):
+    """Large VSS-v0 worlds run the lane-per-match kernel built on the packed fp32x2 forms
+    (FFMA2 / FADD2 / FMUL2, rs_kernel_flags bit 3), small ones the scalar forms (shorter dependent
+    chains).  Each packed half rounds like the scalar instruction and both kernels are compiled from
+    one float2 source, so the choice -- made by world size, hence different for a world and for
+    its shards -- must not change a single bit: 60 steps with contacts, goals and auto-reset."""
+    E = engine
+    monkeypatch.setenv("RS_PER_MATCH", "1")
+    n = 3000
+    a = torch.rand(n, 2, device="cuda") * 2 - 1
+    monkeypatch.setenv("RS_PACKED", "1")
+    p = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=5)
+    assert (p.kernel_flags & 12) == 12
+    monkeypatch.setenv("RS_PACKED", "0")
+    q = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=5)
+    assert (q.kernel_flags & 12) == 4
+    monkeypatch.delenv("RS_PACKED")
+    assert (E.BatchedWorld(0, 0, 3, 3, 25, 65536, seed=5).kernel_flags & 8)
+    assert not (E.BatchedWorld(0, 0, 3, 3, 25, 8192, seed=5).kernel_flags & 8)
+    p.task_reset(E.TASK_VSS_V0); q.task_reset(E.TASK_VSS_V0)
+    for _ in range(60):
+        op = p.vss_env_step(a, max_steps=25)
+        oq = q.vss_env_step(a, max_steps=25)
+        assert all(torch.equal(x, y) for x, y in zip(op, oq))
+    assert torch.equal(p.get_raw(), q.get_raw())
+
+
 def test_host_step_equals_the_device_step_at_a_lane_per_match_size(engine):
     """rs_vss_env_step_host (pinned staging, packed D2H) vs the device-tensor step, bit-exact, at
     a world size that runs the lane-per-match kernels with a ragged last warp."""
