@@ -326,7 +326,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_vss_env_step<3,3,64,true>",
+                         "kernel": "k_vss_env_step<3,3,64,2> (VssF0P: compile-time constants, packed fp32x2 forms)",
                          "alg_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * N,
                          "avg_launch_us": per_launch_s * 1e6},
             "cpu_baseline": cpu,
