@@ -38,8 +38,9 @@ class _BaseVecEnv:
 
     def __init__(self, field_type: int, n_robots_blue: int, n_robots_yellow: int, time_step: float,
                  num_envs: int = 1, device=None, seed: int = 0, env_offset: int = 0, render_mode=None):
-        if render_mode is not None:
-            raise NotImplementedError("rendering is out of scope of rsoccer_b200")
+        if render_mode not in (None, "rgb_array"):
+            raise NotImplementedError("render_mode %r: only 'rgb_array' (no window) is offered" % (render_mode,))
+        self.render_mode = render_mode
         self.num_envs = num_envs
         self.time_step = time_step
         self.rsim = self.RSIM(field_type=field_type, n_robots_blue=n_robots_blue,
@@ -84,8 +85,12 @@ class _BaseVecEnv:
     def close(self):
         self.rsim.stop()
 
-    def render(self):
-        raise NotImplementedError("rendering is out of scope of rsoccer_b200")
+    def render(self, index=0, width_px=750):
+        """RGB picture [H, W, 3] uint8 of match `index` (vss_gym_base.py:148-187, rgb_array mode)."""
+        from ..render import render_rgb
+        row = self.rsim.simulator.get_state()[int(index)].cpu().numpy()
+        return render_rgb(row, self.rsim.simulator.field_params(), "vss" if isinstance(self, VSSBaseVecEnv) else "ssl",
+                          self.n_robots_blue, self.n_robots_yellow, width_px=width_px)
 
     def _get_commands(self, action):
         raise NotImplementedError

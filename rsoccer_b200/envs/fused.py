@@ -37,8 +37,9 @@ class _FusedVecEnv:
 
     def __init__(self, num_envs=1, device=None, seed=0, env_offset=0, auto_reset=True, max_episode_steps=None,
                  field_type=None, render_mode=None):
-        if render_mode is not None:
-            raise NotImplementedError("rendering is out of scope of rsoccer_b200")
+        if render_mode not in (None, "rgb_array"):
+            raise NotImplementedError("render_mode %r: only 'rgb_array' (no window) is offered" % (render_mode,))
+        self.render_mode = render_mode
         self.num_envs = int(num_envs)
         self.auto_reset = bool(auto_reset)
         self.max_episode_steps = int(max_episode_steps or self.MAX_EPISODE_STEPS)
@@ -85,6 +86,13 @@ class _FusedVecEnv:
         a.copy_(torch.as_tensor(actions_np, dtype=torch.float32).reshape(a.shape))
         self._step_host(a, o, r, d, t)
         return o.numpy(), r.numpy(), d.numpy().astype(bool), t.numpy().astype(bool)
+
+    def render(self, index=0, width_px=750):
+        """RGB picture [H, W, 3] uint8 of match `index` (vss_gym_base.py:148-187, rgb_array mode)."""
+        from ..render import render_rgb
+        row = self.world.get_state()[int(index)].cpu().numpy()
+        return render_rgb(row, self.world.field_params(), "vss" if self.KIND == _E.KIND_VSS else "ssl",
+                          self.N_BLUE, self.N_YELLOW, width_px=width_px)
 
     # ---- batched Frame view of the current state (Entities/Frame.py layout)
     @property

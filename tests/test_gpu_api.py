@@ -281,3 +281,23 @@ def test_host_step_equals_the_device_step_at_a_lane_per_match_size(engine):
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy(), d2) and np.array_equal(t1.cpu().numpy(), t2)
     assert torch.equal(env.world.get_raw(), ref.world.get_raw()) and env.world.t == ref.world.t
+
+
+def test_render_rgb_array_of_env_i_of_a_batch(engine):
+    """env.render(index) with render_mode="rgb_array": the picture of ONE match of the batch, drawn from
+    the device state (ball where get_state says it is); a window mode is not offered."""
+    from rsoccer_b200 import envs, render as RR
+    env = envs.make("VSS-v0", num_envs=5, seed=2, render_mode="rgb_array")
+    env.reset()
+    img = env.render(3)
+    st = env.world.get_state()[3].cpu().numpy()
+    f = env.world.field_params()
+    m = 0.1 + f["goal_depth"]
+    sc = 750 / (f["length"] + 2 * m)
+    assert img.shape[1] == 750 and img.dtype == np.uint8
+    assert tuple(img[int((f["width"] / 2 + m - st[1]) * sc), int((st[0] + f["length"] / 2 + m) * sc)]) == RR.ORANGE
+    with pytest.raises(NotImplementedError):
+        envs.make("VSS-v0", num_envs=1, render_mode="human")
+    ssl = envs.make("SSLStaticDefenders-v0", num_envs=2, render_mode="rgb_array")
+    ssl.reset()
+    assert ssl.render(1, width_px=400).shape[1] == 400

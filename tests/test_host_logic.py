@@ -142,3 +142,47 @@ def test_rollout_all_gather_world_size_2_gloo(n_total):
     for p in ps:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _pixel(img, field, x, y, width_px=750, margin_m=0.1):
+    """colour at field point (x, y) [m]; same mapping as rsoccer_b200/render.py"""
+    m = margin_m + field["goal_depth"]
+    sc = width_px / (field["length"] + 2 * m)
+    return tuple(int(v) for v in img[int((field["width"] / 2 + m - y) * sc), int((x + field["length"] / 2 + m) * sc)])
+
+
+@pytest.mark.parametrize("kind", ["vss", "ssl"])
+def test_render_rgb_array_of_one_match(oracle, kind):
+    """rgb_array picture of one match (stands in for Render/ + pygame, vss_gym_base.py:148-187): shape,
+    palette (Render/utils.py:2-15), ball / robots / lines where the state says they are."""
+    from rsoccer_b200 import render as RR
+    O = oracle
+    if kind == "vss":
+        w = O.OracleWorld(O.KIND_VSS, 0, 3, 3, 25, 1)
+        nb, ny, K = 3, 3, 6
+    else:
+        w = O.OracleWorld(O.KIND_SSL, 2, 1, 2, 25, 1)
+        nb, ny, K = 1, 2, 11
+    field = w.field_params()
+    L, W = field["length"], field["width"]
+    st = np.zeros(5 + K * (nb + ny))
+    st[0:2] = (0.25 * L, 0.2 * W)                                    # ball
+    pos = [(-0.3 * L, 0.25 * W, 0.0), (-0.2 * L, -0.3 * W, 90.0), (0.1 * L, -0.1 * W, 200.0),
+           (0.3 * L, -0.3 * W, 180.0), (0.35 * L, 0.3 * W, -45.0), (0.0, 0.35 * W, 10.0)][:nb + ny]
+    for k, (x, y, th) in enumerate(pos):
+        st[5 + K * k: 8 + K * k] = (x, y, th)
+    img = RR.render_rgb(st, field, kind, nb, ny)
+    assert img.dtype == np.uint8 and img.shape[1] == 750 and img.shape[2] == 3
+    assert abs(img.shape[0] / img.shape[1] - (W + 2 * (0.1 + field["goal_depth"])) / (L + 2 * (0.1 + field["goal_depth"]))) < 0.01
+    assert _pixel(img, field, st[0], st[1]) == RR.ORANGE
+    assert _pixel(img, field, 0.45 * L, 0.45 * W) == RR.BG_GREEN
+    assert _pixel(img, field, 0.0, -0.4 * W) == RR.WHITE             # centre line
+    assert _pixel(img, field, L / 2, 0.4 * W) == RR.WHITE            # field outline
+    r = field["rbt_radius"]
+    for k, (x, y, th) in enumerate(pos):
+        c, s = np.cos(np.radians(th)), np.sin(np.radians(th))
+        # a point ahead-left of the centre lies inside the team-coloured tag, off the heading mark
+        px = _pixel(img, field, x + 0.3 * r * c - 0.3 * r * s, y + 0.3 * r * s + 0.3 * r * c)
+        assert px == (RR.BLUE if k < nb else RR.YELLOW), (k, px)
+    with pytest.raises(ValueError):
+        RR.render_rgb(st[:-1], field, kind, nb, ny)
