@@ -26,7 +26,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    n_total, T = 65536 * world + 37, 24
+    # RS_CHECK_PER_RANK=16384: the shards run the scalar-form kernel, the unsharded world the packed one
+    n_total, T = int(os.environ.get("RS_CHECK_PER_RANK", "65536")) * world + 37, 24
     env = make_sharded(envs.VSSVecEnv, n_total, rank, world, device=dev, seed=5, max_episode_steps=9)
     lo, hi = shard_range(n_total, rank, world)
     g = torch.Generator().manual_seed(3)
