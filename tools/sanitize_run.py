@@ -15,9 +15,12 @@ import torch  # noqa: E402
 from rsoccer_b200 import engine as E  # noqa: E402
 
 TASKS = ((0, 0, 0, 3, 3, 2), (1, 1, 2, 1, 6, 5), (2, 1, 2, 1, 1, 5), (3, 1, 2, 1, 4, 4), (4, 1, 2, 2, 0, 3))
-for mode in ("1", "0"):
+for mode, packed in (("1", "1"), ("1", "0"), ("0", "0")):
     os.environ["RS_PER_MATCH"] = mode
+    os.environ["RS_PACKED"] = packed         # VSS-v0 lane-per-match kernel: packed fp32x2 forms + pair table / scalar forms
     for task, kind, ft, nb, ny, nact in TASKS:
+        if packed == "1" and task != 0:
+            continue
         for n in (200, 1):
             w = E.BatchedWorld(kind, ft, nb, ny, 25, n, seed=3)
             w.task_reset(task)
