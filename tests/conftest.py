@@ -29,10 +29,13 @@ def _engine_module():
     return E
 
 
-@pytest.fixture(params=["per_match", "per_body"])
+@pytest.fixture(params=["per_match", "per_match_packed", "per_body"])
 def engine(request, monkeypatch, _engine_module):
-    """The CUDA engine, once per kernel mapping: rs_create reads RS_PER_MATCH (1 = one lane
-    per match, rs_device.cuh; 0 = one lane per body, rs_lanes.cuh; unset = by world size),
-    so every GPU test exercises both families whatever the size heuristic would pick."""
-    monkeypatch.setenv("RS_PER_MATCH", "1" if request.param == "per_match" else "0")
+    """The CUDA engine, once per kernel family: rs_create reads RS_PER_MATCH (1 = one lane
+    per match, rs_device.cuh; 0 = one lane per body, rs_lanes.cuh; unset = by world size) and
+    RS_PACKED (1 = the packed fp32x2 instruction forms of the large-world VSS-v0 kernel, 0 = the
+    scalar forms; unset = by world size), so every GPU test exercises all of them whatever the
+    size heuristics would pick."""
+    monkeypatch.setenv("RS_PER_MATCH", "0" if request.param == "per_body" else "1")
+    monkeypatch.setenv("RS_PACKED", "1" if request.param == "per_match_packed" else "0")
     return _engine_module
