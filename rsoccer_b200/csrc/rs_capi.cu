@@ -808,7 +808,9 @@ k_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, const float
 }
 
 // simulator.step(cmds): physics only, any (kind, R).  RT > 0: register resident scene.
-template <int KIND, int RT, int BS>
+// F0 (VSS 3 v 3 on field 0 at 25 ms only): 1 = compile-time physics constants (VssF0), 2 = the same with the packed
+// fp32x2 forms (VssF0P), as in k_vss_env_step.
+template <int KIND, int RT, int BS, int F0 = 0>
 __global__ void __launch_bounds__(BS)
 k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__restrict__ cmds) {
     const int e = blockIdx.x * BS + threadIdx.x;
@@ -826,7 +828,7 @@ k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__re
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float2 c = c2[r];
-            vss_target(P, c.x, c.y, d.tf[r], d.tw[r]);
+            vss_target<F0 == 2 && VssF0P::packed>(P, c.x, c.y, d.tf[r], d.tw[r]);
             d.tl[r] = 0.0f; d.kick[r] = 0.0f;
         }
     } else {
@@ -844,7 +846,9 @@ k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__re
         // per-lane contact resolve through shared memory (rs_device.cuh): one region per warp
         __shared__ __align__(16) float4 scratch[BS / 32][2 * (RT + 1) * 32];
         float4 *const cq = scratch[threadIdx.x >> 5] + (threadIdx.x & 31);
-        physics_step<KIND, RT>(P, s, d, live, cq, cq + (RT + 1) * 32, 32);
+        if constexpr (F0 == 2) physics_step<KIND, RT>(VssF0P{}, s, d, live, cq, cq + (RT + 1) * 32, 32);
+        else if constexpr (F0 == 1) physics_step<KIND, RT>(VssF0{}, s, d, live, cq, cq + (RT + 1) * 32, 32);
+        else physics_step<KIND, RT>(P, s, d, live, cq, cq + (RT + 1) * 32, 32);
     } else {
         physics_step<KIND, RT>(P, s, d, live);
     }
@@ -1138,6 +1142,13 @@ static void launch_step_kernel(void (*kernel)(KArgs...), int grid, int block, cu
 template <int KIND, int RT>
 static void launch_step(rs_world *w, const float *cmds, cudaStream_t st) {
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
+    if constexpr (KIND == RS_KIND_VSS && RT == VssF0::n_robots) {
+        if (w->f0) {            // rs_create compared the constants bit for bit (matches_vss_f0)
+            if (use_packed(w)) launch_step_kernel(k_step<KIND, RT, 64, 2>, g64, 64, st, w->dp, state_ptrs(w), cmds);
+            else launch_step_kernel(k_step<KIND, RT, 64, 1>, g64, 64, st, w->dp, state_ptrs(w), cmds);
+            return;
+        }
+    }
     if (w->block == 128) launch_step_kernel(k_step<KIND, RT, 128>, g128, 128, st, w->dp, state_ptrs(w), cmds);
     else launch_step_kernel(k_step<KIND, RT, 64>, g64, 64, st, w->dp, state_ptrs(w), cmds);
 }
