@@ -105,11 +105,12 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 // immediate broadcasts into both halves, negation is an operand modifier): two IEEE results per
 // issued instruction, each half rounded exactly like the scalar instruction.  Every (x, y) /
 // (vx, vy) operation of a body -- the halves of the register quad its state was loaded into --
-// can be issued as one instruction.  It pays where a kernel is bound by issue slots (VSS-v0,
-// one lane per match, >= ~20 000 matches: 16.65 -> 15.7 us at 65 536) and costs where it is
-// bound by the dependent latency of a few warps (the packed forms are slower to return: VSS-v0
-// at 4 096 matches 7.24 -> 7.54 us, SSL 1 v 1 at 16 384 7.15 -> 7.27 us), so the source is
-// written once on float2 and the parameter class picks the instruction form (PP::packed).
+// can be issued as one instruction.  Measured (tools/microbench/pk_latency.cu): scalar latency (4.4
+// cycles), two cycles of the FMA pipe per packed instruction -- the same fp32 throughput in half
+// the issue slots.  It pays where a kernel is bound by issue slots (VSS-v0, one lane per match,
+// >= ~20 000 matches: 16.65 -> 15.7 us at 65 536) and not where it is bound by the dependent
+// latency of a few warps (8 192 matches: 7.90 -> 8.02 us), so the source is written once on
+// float2 and the parameter class picks the instruction form (PP::packed).
 __device__ __forceinline__ float2 pk_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 pk_fma(const float2 a, const float2 b, const float2 c) { return __ffma2_rn(a, b, c); }
