@@ -1112,8 +1112,8 @@ static bool use_lane_per_body(const rs_world *w, bool task_kernel) {
 }
 
 // Packed fp32x2 forms (VssF0P, rs_device.cuh) or scalar forms in the VssF0 lane-per-match kernels?  Same
-// results bit for bit (tests/test_gpu_api.py); fewer issued instructions but longer dependent
-// chains, so it is a matter of world size: 16 384 matches 8.21 (scalar) vs 8.30 us (packed), 24 576
+// results bit for bit (tests/test_gpu_api.py); the packed forms save issue slots, which only large worlds are
+// short of, and the pair table adds loads to the contact chain, so it is a matter of world size: 16 384 matches 8.21 (scalar) vs 8.30 us (packed), 24 576
 // matches 9.90 vs 9.50 us, 65 536 matches 17.05 vs 15.71 us (profiles/r1g_packed.txt).  The whole world decides, not
 // the chunk a launch covers.
 #ifndef RS_PACKED_MIN_MATCHES
