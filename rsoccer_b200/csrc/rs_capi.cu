@@ -221,7 +221,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 // CTA.  Same launch contract as k_vss_env_step.  The eight task words of a match (previous
 // potential, step counter, six reward_shaping_total accumulators) are one word per lane:
 // one load and one store instruction for all of them.
-template <int BS>
+template <int BS, bool F0 = false /* physics constants are VssF0's immediates */>
 __global__ void __launch_bounds__(BS)
 k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
     constexpr int L = 8, NB = 3, NY = 3, R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
@@ -282,7 +282,8 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
         reinterpret_cast<float2 *>(A.cmds_out)[(size_t)e * R + (b - 1)] = make_float2(wl, wr);
 
     // ---- rsim.send_commands + get_frame, vss_gym_base.py:77-82
-    lanes_physics_step<RS_KIND_VSS, L>(P, R, b, s, d);
+    if constexpr (F0) lanes_physics_step<RS_KIND_VSS, L>(VssF0{}, R, b, s, d);
+    else lanes_physics_step<RS_KIND_VSS, L>(P, R, b, s, d);
 
     // ---- _calculate_reward_and_done, vss_gym.py:144-192: every lane evaluates it on the
     // ball (lane 0) and blue 0 (lane 1) and keeps the update of its own task word
@@ -775,7 +776,7 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
 }
 
 // simulator.step(cmds), one lane per BODY: any (kind, R <= 31) with L = 2^k >= R + 1
-template <int KIND, int L, int BS>
+template <int KIND, int L, int BS, bool F0 = false /* VSS 3 v 3, field 0, 25 ms: VssF0's immediates */>
 __global__ void __launch_bounds__(BS)
 k_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, const float *__restrict__ cmds) {
     const int R = P.n_robots;
@@ -803,7 +804,8 @@ k_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, const float
         }
     }
     __syncwarp();
-    lanes_physics_step<KIND, L>(P, R, b, s, d);
+    if constexpr (F0) lanes_physics_step<KIND, L>(VssF0{}, R, b, s, d);
+    else lanes_physics_step<KIND, L>(P, R, b, s, d);
     if (valid) lanes_store<L>(S, R, b, e, s);
 }
 
@@ -1159,6 +1161,7 @@ static void launch_step_lanes_l(rs_world *w, const float *cmds, cudaStream_t st)
     const StatePtrs S = state_ptrs(w);
     if (w->lane_block == 256) launch_step_kernel(k_step_lanes<KIND, L, 256>, (w->n + 256 / L - 1) / (256 / L), 256, st, w->dp, S, cmds);
     else if (w->lane_block == 64) launch_step_kernel(k_step_lanes<KIND, L, 64>, (w->n + 64 / L - 1) / (64 / L), 64, st, w->dp, S, cmds);
+    else if (KIND == RS_KIND_VSS && L == 8 && w->f0) launch_step_kernel(k_step_lanes<RS_KIND_VSS, 8, 128, true>, (w->n + 15) / 16, 128, st, w->dp, S, cmds);
     else launch_step_kernel(k_step_lanes<KIND, L, 128>, (w->n + 128 / L - 1) / (128 / L), 128, st, w->dp, S, cmds);
 }
 template <int KIND>
@@ -1411,6 +1414,7 @@ static void launch_vss(rs_world *w, const VssStepArgs &A, const StatePtrs &S, cu
     if (use_lane_per_body(w, true)) {
         if (w->lane_block == 256) launch_step_kernel(k_vss_env_step_lanes<256>, (n + 31) / 32, 256, st, w->dp, S, A);
         else if (w->lane_block == 64) launch_step_kernel(k_vss_env_step_lanes<64>, (n + 7) / 8, 64, st, w->dp, S, A);
+        else if (w->f0) launch_step_kernel(k_vss_env_step_lanes<128, true>, (n + 15) / 16, 128, st, w->dp, S, A);
         else launch_step_kernel(k_vss_env_step_lanes<128>, (n + 15) / 16, 128, st, w->dp, S, A);
     } else if (w->f0 && use_packed(w)) switch (w->block) {
         case 32: launch_step_kernel(k_vss_env_step<3, 3, 32, 2>, (n + 31) / 32, 32, st, w->dp, S, A); break;

@@ -60,8 +60,8 @@ __device__ __forceinline__ float dist2(float dx, float dy) { return dx * dx + dy
 // One contact (i < j, body indices) of this group; every lane of the group computes it from
 // shuffled copies, lanes i and j keep their side.  Positions are those of the phase start
 // (corrections accumulate in cx, cy); velocities are live (sequential impulses).
-template <int KIND, int L>
-__device__ __forceinline__ void lanes_resolve(const DevParams &P, const LaneGroup<L> &g, const int b,
+template <int KIND, int L, class PP>
+__device__ __forceinline__ void lanes_resolve(const PP &P, const LaneGroup<L> &g, const int b,
                                               const int i, const int j, LaneBody &s, float &cx, float &cy) {
     const float xi = g.gget(s.x, i), yi = g.gget(s.y, i), xj = g.gget(s.x, j), yj = g.gget(s.y, j);
     float vxi = g.gget(s.vx, i), vyi = g.gget(s.vy, i), vxj = g.gget(s.vx, j), vyj = g.gget(s.vy, j);
@@ -80,8 +80,9 @@ __device__ __forceinline__ void lanes_resolve(const DevParams &P, const LaneGrou
 
 // one control step (RS_SUBSTEPS sub-steps) of the match this lane's group holds.
 //   b: body index of this lane (0 ball, 1..R robots, > R idle); idle lanes carry zeros.
-template <int KIND, int L>
-__device__ __forceinline__ void lanes_physics_step(const DevParams &P, const int R, const int b,
+// PP = DevParams (run-time constants) or VssF0 (the benchmark world: immediates, VSS only)
+template <int KIND, int L, class PP>
+__device__ __forceinline__ void lanes_physics_step(const PP &P, const int R, const int b,
                                                    LaneBody &s, const LaneDrive &d) {
     constexpr int ND = LaneGroup<L>::ND;
     const LaneGroup<L> g;
@@ -100,7 +101,7 @@ __device__ __forceinline__ void lanes_physics_step(const DevParams &P, const int
     }
 
     bool kicked = false;
-    if (KIND == RS_KIND_SSL) {
+    if constexpr (KIND == RS_KIND_SSL) {
         // kick: once per control step; robots in row order overwrite the ball velocity, so
         // the highest kicking row that touches the ball wins
         const bool wants = is_robot && d.kick > 0.0f;
@@ -137,7 +138,7 @@ __device__ __forceinline__ void lanes_physics_step(const DevParams &P, const int
         // (b) dribbler latch: first robot in row order with the dribbler on, not kicking,
         // and the ball in its kicker box holds the ball for this sub-step
         int holder = -1; float hx = 0.0f, hy = 0.0f;
-        if (KIND == RS_KIND_SSL) {
+        if constexpr (KIND == RS_KIND_SSL) {
             const bool cand = is_robot && d.drib && !kicked;
             if (__any_sync(RS_FULL_MASK, cand)) {
                 const float dx = g.get(s.x, 0) - s.x, dy = g.get(s.y, 0) - s.y;
@@ -162,7 +163,7 @@ __device__ __forceinline__ void lanes_physics_step(const DevParams &P, const int
             s.x += s.vx * hh; s.y += s.vy * hh;
             s.th = wrap_pi(s.th + s.om * h);
         }
-        if (KIND == RS_KIND_SSL) {
+        if constexpr (KIND == RS_KIND_SSL) {
             if (__any_sync(RS_FULL_MASK, holder >= 0)) {
                 float s2, c2;
                 __sincosf(s.th, &s2, &c2);
