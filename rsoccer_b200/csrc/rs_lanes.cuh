@@ -124,8 +124,9 @@ __device__ __forceinline__ void lanes_physics_step(const PP &P, const int R, con
         // (a) drive: velocity in the robot frame moves toward the target, traction limited
         float vf = cs * s.vx + sn * s.vy, vl = -sn * s.vx + cs * s.vy;
         if (KIND == RS_KIND_VSS) {
-            vf += clampf(d.tf - vf, -P.acc_fwd_h, P.acc_fwd_h);
-            vl += clampf(d.tl - vl, -P.acc_lat_h, P.acc_lat_h);
+            // v + clamp(t - v, -a, a) == clamp(t, v - a, v + a): two independent adds, then min / max (a shorter chain)
+            vf = fmaxf(fminf(d.tf, vf + P.acc_fwd_h), vf - P.acc_fwd_h);
+            vl = fmaxf(fminf(d.tl, vl + P.acc_lat_h), vl - P.acc_lat_h);
         } else {
             const float df = d.tf - vf, dl = d.tl - vl;
             const float n2 = df * df + dl * dl;
@@ -133,7 +134,7 @@ __device__ __forceinline__ void lanes_physics_step(const PP &P, const int R, con
             if (n2 > P.acc_fwd_h * P.acc_fwd_h) sc = P.acc_fwd_h * rsqrtf(n2);
             vf += df * sc; vl += dl * sc;
         }
-        const float om_n = s.om + clampf(d.tw - s.om, -P.acc_ang_h, P.acc_ang_h);
+        const float om_n = fmaxf(fminf(d.tw, s.om + P.acc_ang_h), s.om - P.acc_ang_h);
         const float dvx = cs * vf - sn * vl, dvy = sn * vf + cs * vl;
         // (b) dribbler latch: first robot in row order with the dribbler on, not kicking,
         // and the ball in its kicker box holds the ball for this sub-step
@@ -209,8 +210,9 @@ __device__ __forceinline__ void lanes_physics_step(const PP &P, const int R, con
             }
             __syncwarp();
         }
-        // (f) walls
-        walls<KIND>(P, rad, ew, s.x, s.y, s.vx, s.vy);
+        // (f) walls (VSS: the lean form of the lane-per-match kernels, same decisions and arithmetic)
+        if constexpr (KIND == RS_KIND_VSS) vss_walls(P, rad, ew, s.x, s.y, s.vx, s.vy);
+        else walls<KIND>(P, rad, ew, s.x, s.y, s.vx, s.vy);
     }
 }
 
