@@ -116,3 +116,42 @@ print("OK")
 ''' % (ROOT, os.path.join(ROOT, "tests", "golden", "shims"), REF)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_oracle_physics_is_mirror_symmetric(oracle):
+    """The model is symmetric under y -> -y (theta -> -theta, omega -> -omega, wheels swapped); so is the fp64
+    arithmetic of the oracle: VSS worlds stay mirror images bit for bit through contacts and walls (the CUDA
+    kernels keep the same property, tests/test_gpu_parity.py).  SSL worlds do so only without drive commands:
+    the omni wheel matrices are rounded from cos / sin of the wheel angles and are symmetric to an ulp."""
+    O = oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity import random_raw
+    rng = np.random.default_rng(12)
+
+    def run(kind, ft, nb, ny, n, steps, drive):
+        R = nb + ny
+        a, b = O.OracleWorld(kind, ft, nb, ny, 25, n, seed=1), O.OracleWorld(kind, ft, nb, ny, 25, n, seed=1)
+        fp = a.field_params()
+        raw = random_raw(rng, n, R, fp["length"] / 2, fp["width"] / 2)
+        sign = np.ones(4 + 6 * R)
+        sign[[1, 3]] = -1
+        for r in range(R):
+            sign[[4 + 6 * r + 1, 4 + 6 * r + 2, 4 + 6 * r + 4, 4 + 6 * r + 5]] = -1
+        a.set_raw(raw); b.set_raw(raw * sign)
+        for _ in range(steps):
+            if kind == O.KIND_VSS:
+                c = rng.uniform(-60, 60, (n, R, 2))
+                a.step(c); b.step(c[:, :, ::-1].copy())
+            else:
+                c = np.zeros((n, R, 8))
+                if drive:
+                    c[:, :, 1:3] = rng.uniform(-2.5, 2.5, (n, R, 2)); c[:, :, 3] = rng.uniform(-10, 10, (n, R))
+                a.step(c); b.step(c * np.array([1, 1, -1, -1, 1, 1, 1, 1.0]))
+        ra, rb = a.get_raw(), b.get_raw() * sign
+        assert np.abs(ra[:, :2] - raw[:, :2]).max() > 0.01
+        return int((ra != rb).any(axis=1).sum()), float(np.abs(ra - rb).max())
+
+    assert run(O.KIND_VSS, 0, 3, 3, 512, 40, True)[0] == 0
+    assert run(O.KIND_SSL, 2, 1, 6, 256, 10, False)[0] == 0
+    bad, worst = run(O.KIND_SSL, 2, 1, 6, 256, 2, True)
+    assert worst < 1e-12                     # symmetric to rounding, not to the bit
