@@ -428,3 +428,34 @@ def test_vss_step_keeps_a_world_and_its_mirror_image_mirror_images(engine, n):
     moved = float((ra[:, :2] - torch.tensor(raw[:, :2], device="cuda")).abs().max())
     assert moved > 0.05                      # the worlds did evolve
     assert bad == 0, "%d of %d matches lost the mirror symmetry" % (bad, n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [4096, 40000])
+def test_vss_env_step_keeps_a_world_and_its_mirror_image_mirror_images(engine, n):
+    """The reflection property through the whole fused VSSEnv.step: with the action components swapped and the OU
+    normals of each robot swapped (supplied explicitly; no auto-reset, whose placement draws are not mirrored),
+    commands, physics, reward, done and the observation rows of a world and of its mirror image stay mirror
+    images bit for bit for 30 steps (observation: y, sin(theta), v_y, omega change sign)."""
+    E = engine
+    R = 6
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a, b = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=2), E.BatchedWorld(0, 0, 3, 3, 25, n, seed=2)
+    a.task_reset(E.TASK_VSS_V0); b.task_reset(E.TASK_VSS_V0)
+    sign = torch.ones(4 + 6 * R)
+    sign[[1, 3]] = -1.0
+    for r in range(R):
+        sign[[4 + 6 * r + 1, 4 + 6 * r + 2, 4 + 6 * r + 4, 4 + 6 * r + 5]] = -1.0
+    sign = sign.cuda()
+    osign = torch.tensor([1, -1, 1, -1] + [1, -1, -1, 1, 1, -1, -1] * 3 + [1, -1, 1, -1, -1] * 3, dtype=torch.float32).cuda()
+    b.set_raw(a.get_raw() * sign)
+    worst_rew = 0.0
+    for _ in range(30):
+        act = (torch.rand(n, 2, generator=g) * 2 - 1).cuda()
+        z = torch.randn(n, R - 1, 2, generator=g).cuda()
+        oa, ra, da, _ = a.vss_env_step(act, normals=z.reshape(n, -1), auto_reset=False, max_steps=10 ** 6)
+        ob, rb, db, _ = b.vss_env_step(act.flip(-1).contiguous(), normals=z.flip(-1).reshape(n, -1).contiguous(),
+                                       auto_reset=False, max_steps=10 ** 6)
+        assert torch.equal(oa, ob * osign) and torch.equal(da, db)
+        assert torch.equal(ra, rb)
+    assert torch.equal(a.get_raw(), b.get_raw() * sign)
