@@ -1556,7 +1556,8 @@ static int host_epilogue(rs_world *w, int obs_dim, float *h_obs, float *h_reward
 // 54 GB/s a pinned copy reaches here) is 80 % of the call; two alternatives were measured on
 // B200 and are slower than this plain form (251 us per step): four sub-range launches pipelined
 // against four smaller copies on a second stream (284 us: the smaller copies lose more than
-// the 17 us kernel hides) and the kernel storing straight into the mapped host buffers (267 us).
+// the 17 us kernel hides), the kernel storing straight into the mapped host buffers (267 us), and (round 1g)
+// the packed copy as two halves on two streams / copy engines (239 vs 234 us: one link, one more launch).
 int rs_vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset, int max_steps,
                          float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc,
                          void *stream) {
