@@ -153,7 +153,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 // ((x >> 8) + 0.5) / 2^24 as one FMA: scaling by a power of two commutes with rounding, so this is bit for
-// bit the add-then-multiply form the oracle uses
+// bit the fp32 add-then-multiply form (= the oracle's fp64 value rounded to fp32)
 __device__ __forceinline__ float u01(uint32_t x) { return fmaf((float)(x >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f); }
 
 struct Rng {   // sequential u32 stream for (env, t, stream): counter (env, t, stream, j)
