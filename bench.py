@@ -1,25 +1,37 @@
 #!/usr/bin/env python
-"""bench.py -- env.step()/sec of VSS-v0 3v3 at 65 536 envs per GPU (BASELINE.json metric).
+"""bench.py -- env.step()/sec of the batched robot-soccer engine (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
   python bench.py --impl reference ...                        # the CPU path, same metric
+  python bench.py --config {vss65536,vss4096,sd4096,cp16384,vss262144_sharded,vss65536_strong}
 
-One "step" = ONE fused launch advancing all 65 536 matches of one world by one control
-step: OU commands + action->wheel conversion, 5 physics sub-steps, observation, reward,
-done, truncation, info accumulators, masked auto-reset (rs_vss_env_step).
+One "step" = ONE fused launch advancing every match of one world by one control step:
+commands (agent action + OU noise), 5 physics sub-steps, observation, reward, done,
+truncation, info accumulators, masked auto-reset (rs_vss_env_step / rs_ssl_env_step).
 
-L2 hygiene: one world's per-step traffic (38.8 MB) fits the 126 MB L2, so the timed loop
-rotates over M independent worlds (default 8 -> 310 MB of state+outputs) and each world is
-touched again only after 7 other worlds streamed through: every step reads its state from
-HBM ("inputs larger than L2").  The K steps are replayed from ONE captured CUDA graph (the
-Philox step counter lives in device memory, so replays draw fresh noise).
+What is timed.  The K steps of the command line are captured into ONE CUDA graph (the Philox
+step counter lives in device memory, so replays draw fresh noise) and the graph is replayed
+`repeats` times, until the timed region holds >= --min-ms of device time: a 20-step region
+is 0.3 ms, far too short for CUDA events, so ms_per_step = total / (K x repeats).  `steps`,
+`repeats`, `warmup` (W direct launches right before the timed region) and `settle_steps` (the
+untimed steps that bring every world to its steady-state contact density, robots leaning on
+walls: freshly reset scenes step ~25 % faster) are all reported; config.launch says what ran.
 
-N > 1: one process per GPU (torchrun), each rank owns its own 65 536-env worlds (global
-env ids are disjoint, "weak" scaling), no collective on the step path; the ranks meet only
-at the barrier around the timed region and at the max-over-ranks of the device time.
+L2 hygiene: one world's per-step traffic (38.8 MB at 65 536 matches) fits the 126 MB L2, so
+the steps rotate over M independent worlds whose combined traffic exceeds 1.6 x L2, and the
+graph length is a multiple of M: every step reads its state from HBM ("inputs larger than
+L2").
+
+N > 1: one process per GPU (torchrun), each rank owns its own worlds (global env ids are
+disjoint, "weak" scaling), no collective on the step path; the ranks meet only at the barrier
+around the timed region and at the max-over-ranks of the device time.  The default line also
+carries `configs` (BASELINE configs 2-5 at the sizes BASELINE.json names), `strong` (the
+literal "65 536 envs on N GPUs": 65 536 / N per GPU) and, for N > 1, `gather` (the rollout
+all-gather over NCCL, alone and overlapped with the next rollout on a side stream).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -30,10 +42,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ENVS_PER_GPU = 65536
-ALG_BYTES_PER_ENV_STEP = 592          # SURVEY.md section 8(d), VSS-v0
-METRIC = "env.step()/sec at 65536 VSS-v0 3v3 envs"
 UNIT = "env-steps/s"
+METRIC = "env.step()/sec at 65536 VSS-v0 3v3 envs"
+L2_BYTES = 126e6
+
+# algorithmic bytes per env-step; BASELINE.json configs 2-5
+CONFIGS = {
+    "vss65536": dict(task="vss", envs=65536, alg=592, max_steps=1200, settle=600,
+                     workload="VSS-v0 3v3, 65536 envs per GPU"),
+    "vss4096": dict(task="vss", envs=4096, alg=592, max_steps=1200, settle=600,
+                    workload="VSS-v0 3v3, 4096 envs (BASELINE config 2)"),
+    "sd4096": dict(task="sd", envs=4096, alg=556, max_steps=1000, settle=300,
+                   workload="SSLStaticDefenders-v0, 4096 envs (BASELINE config 3)"),
+    "cp16384": dict(task="cp", envs=16384, alg=276, max_steps=1200, settle=300,
+                    workload="SSLContestedPossession-v0, 16384 envs (BASELINE config 4)"),
+    "vss262144_sharded": dict(task="vss", envs=32768, alg=592, max_steps=1200, settle=600,
+                              workload="VSS-v0 3v3, 32768 envs per GPU (BASELINE config 5: 262144 over 8 GPUs)"),
+    "vss65536_strong": dict(task="vss", envs=None, alg=592, max_steps=1200, settle=600,
+                            workload="VSS-v0 3v3, 65536 envs in total, split over the GPUs"),
+}
 
 
 def _peaks():
@@ -43,6 +70,10 @@ def _peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -58,7 +89,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -72,7 +103,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -96,66 +127,149 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_run(threads, target_seconds, envs=4096):
-    """The CPU path on the host cores: the oracle's restatement of VSSEnv.step (kind "port";
-    robosim itself -- the reference's engine -- cannot be installed, DESIGN.md section 6)."""
-    import numpy as np
+# ----------------------------------------------------------------------------- CPU arms
+def _oracle_world(task, envs, threads):
     from oracle import oracle as O
     O.build()
-    # num_threads() in the oracle's omp pragma overrides OMP_NUM_THREADS (torchrun sets it to 1)
     threads = O.usable_threads(threads)
-    w = O.OracleWorld(O.KIND_VSS, 0, 3, 3, 25, envs, seed=1, threads=threads)
-    w.task_reset(O.TASK_VSS)
-    rng = np.random.default_rng(0)
-    act = rng.uniform(-1, 1, (envs, 2)).astype(np.float32)
+    if task == "vss":
+        w = O.OracleWorld(O.KIND_VSS, 0, 3, 3, 25, envs, seed=1, threads=threads)
+        tid, ad, ms = O.TASK_VSS, 2, 1200
+    elif task == "sd":
+        w = O.OracleWorld(O.KIND_SSL, 2, 1, 6, 25, envs, seed=1, threads=threads)
+        tid, ad, ms = O.TASK_SSL_STATIC_DEFENDERS, 5, 1000
+    else:
+        w = O.OracleWorld(O.KIND_SSL, 2, 1, 1, 25, envs, seed=1, threads=threads)
+        tid, ad, ms = O.TASK_SSL_CONTESTED_POSSESSION, 5, 1200
+    w.task_reset(tid)
+    import numpy as np
+    act = np.random.default_rng(0).uniform(-1, 1, (envs, ad)).astype(np.float32)
+    if task == "vss":
+        return w, threads, (lambda: w.vss_env_step(act, max_steps=ms))
+    return w, threads, (lambda: w.ssl_env_step(tid, act, max_steps=ms))
+
+
+def cpu_baseline_run(task, threads, target_seconds, envs=4096):
+    """The CPU path on the host cores: the oracle's restatement of the env's step (kind "port";
+    robosim itself -- the reference's engine -- cannot be installed, DESIGN.md section 6)."""
+    w, threads, step = _oracle_world(task, envs, threads)
     for _ in range(3):
-        w.vss_env_step(act)
+        step()
     t0 = time.perf_counter()
-    w.vss_env_step(act)
+    step()
     one = max(time.perf_counter() - t0, 1e-6)
     steps = int(max(5, min(20000, target_seconds / one)))
     t0 = time.perf_counter()
     for _ in range(steps):
-        w.vss_env_step(act)
+        step()
     dt = time.perf_counter() - t0
     return {"value": envs * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d VSS-v0 envs x %d steps of oracle/rs_oracle.c (fp64 C, OpenMP) in %.1f s"
-                      % (envs, steps, dt)}
+            "sample": "%d envs x %d steps of oracle/rs_oracle.c (fp64 C, OpenMP) in %.1f s" % (envs, steps, dt)}
 
 
-def run_reference(args, rank, world, out):
-    """--impl reference: the CPU path, all host threads, bounded sample per step."""
+def reference_vssenv_run(target_seconds=4.0):
+    """the UNMODIFIED reference VSSEnv (its Python wrapper:
+    vss_gym.py:89, vss_gym_base.py:72) stepping one env, engine = the oracle behind the robosim
+    stand-in.  Needs the reference package installed under baseline/_ref (build() does that when
+    /root/reference is present); returns None otherwise."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "rsoccer_gym")):
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden", "shims"))
+        import robosim as oracle_robosim          # tests/golden/shims: `robosim` served by the oracle
+        from rsoccer_b200 import compat
+        compat.install(robosim_module=oracle_robosim)      # + gymnasium / pygame stand-ins when those are absent
+        sys.path.insert(0, ref)
+        import gymnasium as gym
+        import rsoccer_gym           # noqa: F401  (the unmodified reference package)
+        import numpy as np
+        env = gym.make("VSS-v0")
+        env.reset()
+        rng = np.random.default_rng(0)
+        for _ in range(50):
+            env.step(rng.uniform(-1, 1, 2).astype(np.float32))
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < target_seconds:
+            for _ in range(100):
+                _, _, done, trunc, _ = env.step(rng.uniform(-1, 1, 2).astype(np.float32))
+                if done or trunc:
+                    env.reset()
+            n += 100
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": UNIT, "cores": 1, "us_per_step": 1e6 * dt / n,
+                "what": "unmodified reference VSSEnv.step (gym.make('VSS-v0'), 1 env, 1 process), engine = "
+                        "oracle/rs_oracle.c behind the robosim stand-in: Python wrapper + physics"}
+    except Exception as e:       # the arm must never take the bench down
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
+def run_reference(args, rank, out):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+    robosim (rc-robosim) is tried first; it is absent from this image, so the
+    arm times the CPU restatement (oracle/rs_oracle.c, all host threads) at the FULL config size:
+    K steps of 65 536 envs, repeated until >= 2 s are timed."""
     if rank != 0:
         return
-    import numpy as np
-    from oracle import oracle as O
-    O.build()
-    threads = O.usable_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    envs = 8192
-    w = O.OracleWorld(O.KIND_VSS, 0, 3, 3, 25, envs, seed=1, threads=threads)
-    w.task_reset(O.TASK_VSS)
-    rng = np.random.default_rng(0)
-    act = rng.uniform(-1, 1, (envs, 2)).astype(np.float32)
-    steps = min(args.steps, 400)
-    warm = min(args.warmup, 20)
-    for _ in range(warm):
-        w.vss_env_step(act)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        w.vss_env_step(act)
-    dt = time.perf_counter() - t0
-    v = envs * steps / dt
+    cfg = CONFIGS[args.config]
+    envs = cfg["envs"] or 65536
+    K, W = max(1, args.steps), max(0, args.warmup)
+    threads = _host_threads()
+    try:
+        import robosim  # noqa: F401
+        have_robosim = True
+    except Exception:
+        have_robosim = False
+    if have_robosim and cfg["task"] == "vss":
+        # the real thing: gym.make('VSS-v0') random-action loop, one process (README.md:116-133)
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        import gymnasium as gym
+        import numpy as np
+        import rsoccer_gym  # noqa: F401
+        env = gym.make("VSS-v0")
+        env.reset()
+        rng = np.random.default_rng(0)
+        for _ in range(W):
+            env.step(rng.uniform(-1, 1, 2).astype(np.float32))
+        reps, t0 = 0, time.perf_counter()
+        while reps == 0 or time.perf_counter() - t0 < 2.0:
+            for _ in range(K):
+                _, _, d, tr, _ = env.step(rng.uniform(-1, 1, 2).astype(np.float32))
+                if d or tr:
+                    env.reset()
+            reps += 1
+        dt = time.perf_counter() - t0
+        v, kind, threads = K * reps / dt, "reference", 1
+        sample = "rSim: gym.make('VSS-v0'), 1 env, 1 process, %d steps in %.1f s" % (K * reps, dt)
+        ms_per_step = 1e3 * dt / (K * reps)
+    else:
+        w, threads, step = _oracle_world(cfg["task"], envs, threads)
+        for _ in range(max(W, 1)):
+            step()
+        reps, t0 = 0, time.perf_counter()
+        while reps == 0 or time.perf_counter() - t0 < 2.0:
+            for _ in range(K):
+                step()
+            reps += 1
+        dt = time.perf_counter() - t0
+        v, kind = envs * K * reps / dt, "port"
+        sample = "%d envs x %d steps x %d repeats in %.1f s, OpenMP %d threads" % (envs, K, reps, dt, threads)
+        ms_per_step = 1e3 * dt / (K * reps)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "steps": K, "repeats": reps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "VSS-v0 3v3, 65536 envs per GPU",
-                   "note": "robosim (rc-robosim 1.2.0) is not installable here; this arm times the "
-                           "CPU restatement of the same path (oracle/rs_oracle.c) on a bounded sample"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d envs x %d steps per run, OpenMP %d threads" % (envs, steps, threads)},
+        "config": {"workload": cfg["workload"],
+                   "robosim": "imported" if have_robosim else "absent (rc-robosim 1.2.0 is not installable here)",
+                   "note": "rSim timed through the unmodified reference env" if have_robosim else
+                           "this arm times the CPU restatement of the same path (oracle/rs_oracle.c, fp64, OpenMP) "
+                           "at the full config size; it is not rSim"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    wrapped = reference_vssenv_run(3.0) if cfg["task"] == "vss" and not have_robosim else None
+    if wrapped is not None:
+        line["reference_vssenv"] = wrapped
     print(json.dumps(line), file=out, flush=True)
 
 
@@ -170,22 +284,302 @@ def _claim_stdout():
     return out
 
 
+# ----------------------------------------------------------------------------- host placement
+def bind_near_gpu(torch, index):
+    """Pin this process to the CPUs of its GPU's NUMA node BEFORE it allocates pinned memory (first
+    touch then places the e2e landing zone next to the GPU's PCIe root).  Returns what it found."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        with open(base + "/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(base + "/local_cpulist") as f:
+            cl = f.read().strip()
+        info["cpus"] = cl
+        cpus = set()
+        for part in cl.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+        info["n_cpus"] = len(use or allowed)
+    except Exception as e:
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
+# ----------------------------------------------------------------------------- GPU workloads
+class Workload:
+    """M independent worlds of one config on this rank's GPU, stepped round-robin."""
+
+    def __init__(self, torch, E, name, cfg, envs, dev, rank, overlap, K, seed_base=0):
+        from rsoccer_b200 import _lib
+        self.torch, self.E, self.name, self.cfg, self.N, self.dev = torch, E, name, cfg, envs, dev
+        self.task = cfg["task"]
+        # combined per-pass traffic >= 2.4 x L2 (8 worlds at 65 536 matches); the graph holds lcm(K, M) steps, so
+        # that a replay continues the rotation where the previous one stopped: M is the first count that keeps it short
+        m0 = max(2, int(math.ceil(2.4 * L2_BYTES / (envs * cfg["alg"]))))
+        self.M = next((m for m in range(m0, m0 + 4 * K + 1) if K * m // math.gcd(K, m) <= 4096), m0)
+        self.G = K * self.M // math.gcd(K, self.M)
+        self.worlds, self.acts, self.outs = [], [], []
+        gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+        for m in range(self.M):
+            off = ((seed_base * 64 + rank) * self.M + m) * envs
+            if self.task == "vss":
+                w = E.BatchedWorld(E.KIND_VSS, 0, 3, 3, 25, envs, device=dev, seed=2024, env_offset=off)
+                self.tid, ad = E.TASK_VSS_V0, 2
+            elif self.task == "sd":
+                w = E.BatchedWorld(E.KIND_SSL, 2, 1, 6, 25, envs, device=dev, seed=2024, env_offset=off)
+                self.tid, ad = E.TASK_SSL_STATIC_DEFENDERS_V0, 5
+            else:
+                w = E.BatchedWorld(E.KIND_SSL, 2, 1, 1, 25, envs, device=dev, seed=2024, env_offset=off)
+                self.tid, ad = E.TASK_SSL_CONTESTED_POSSESSION_V0, 5
+            w.set_option(_lib.OPT_STEP_OVERLAP, overlap)
+            w.task_reset(self.tid)
+            self.worlds.append(w)
+            self.acts.append((torch.rand(envs, ad, generator=gen) * 2 - 1).to(dev))
+            self.outs.append(w.alloc_outputs(self.tid))
+        self.act_dim, self.obs_dim = ad, self.worlds[0].obs_dim(self.tid)
+        self.overlap = overlap
+        flags = self.worlds[0].kernel_flags
+        if self.task == "vss":
+            self.kernel = ("k_vss_env_step_lanes<128,F0> (one lane per body)" if flags & 1 else
+                           "k_vss_env_step<3,3,64,%d> (one lane per match%s)" % (2 if flags & 8 else 1,
+                                                                                  ", packed fp32x2 forms" if flags & 8 else ""))
+        else:
+            nbny = "1,6" if self.task == "sd" else "1,1"
+            self.kernel = ("k_ssl_env_step_lanes<%s> (one lane per body)" % nbny if flags & 1 else
+                           "k_ssl_env_step<%s,64> (one lane per match)" % nbny)
+
+    def step(self, i):
+        m = i % self.M
+        if self.task == "vss":
+            self.worlds[m].vss_env_step(self.acts[m], out=self.outs[m], max_steps=self.cfg["max_steps"])
+        else:
+            self.worlds[m].ssl_env_step(self.tid, self.acts[m], out=self.outs[m], max_steps=self.cfg["max_steps"])
+
+    def set_overlap(self, mode):
+        from rsoccer_b200 import _lib
+        for w in self.worlds:
+            w.set_option(_lib.OPT_STEP_OVERLAP, mode)
+        self.overlap = mode
+
+    def capture(self, stream):
+        torch = self.torch
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for i in range(self.G):
+                self.step(i)
+        return g, self.G
+
+    def host_step(self, bufs):
+        w0 = self.worlds[0]
+        if self.task == "vss":
+            w0.vss_env_step_host(*bufs, max_steps=self.cfg["max_steps"])
+        else:
+            w0.ssl_env_step_host(self.tid, *bufs, max_steps=self.cfg["max_steps"])
+
+    def close(self):
+        for w in self.worlds:
+            w.close()
+        self.worlds = []
+
+
+def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_steps=50, clock_index=None):
+    """settle -> capture -> W warm-up launches -> timed graph replays; then the e2e loop."""
+    res = {}
+    with torch.cuda.stream(stream):
+        if settle:
+            for i in range(wl.cfg["settle"] * wl.M):
+                wl.step(i)
+        stream.synchronize()
+        graph, G = wl.capture(stream)
+        graph.replay()
+        for i in range(W):
+            wl.step(i)
+        # size the timed region
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); graph.replay(); e1.record(stream)
+        stream.synchronize()
+        one = max(e0.elapsed_time(e1), 1e-3)
+    replays = max(1, int(math.ceil(min_ms / one)))
+    if world > 1:
+        t = torch.tensor([replays], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        replays = int(t.item())
+    sampler = None
+    if clock_index is not None:
+        sampler = ClockSampler(clock_index)
+        sampler.start()
+        time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(replays):
+            graph.replay()
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if sampler is not None:
+        res["clocks"] = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    steps_timed = replays * G
+    res.update(ms_total=ms, steps_timed=steps_timed, graph_len=G, replays=replays,
+               ms_per_step=ms / steps_timed, repeats=steps_timed / K)
+
+    # ---- e2e: the public host-buffer call, pinned host memory, H2D + D2H inside the timing
+    if e2e_steps > 0:
+        w0 = wl.worlds[0]
+        N = wl.N
+        h_act = torch.empty(N, wl.act_dim, dtype=torch.float32).pin_memory()
+        h_act.copy_(wl.acts[0].cpu())
+        h_out = w0.alloc_host_outputs(wl.tid)                   # one pinned block -> one D2H copy
+        bufs = (h_act,) + tuple(h_out)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                wl.host_step(bufs)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(e2e_steps):
+                wl.host_step(bufs)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        ms_e = e0.elapsed_time(e1)
+        # the box's own ceiling for this transfer: plain D2H copies of the same block, all ranks at once
+        d2h = N * (wl.obs_dim * 4 + 4 + 1 + 1)
+        dsrc = torch.empty(d2h, dtype=torch.uint8, device=dev)
+        hdst = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                hdst.copy_(dsrc, non_blocking=True)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for _ in range(e2e_steps):
+                hdst.copy_(dsrc, non_blocking=True)
+                stream.synchronize()
+            c1.record(stream)
+            torch.cuda.synchronize()
+        ms_c = c0.elapsed_time(c1)
+        if world > 1:
+            t = torch.tensor([ms_e, ms_c], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e, ms_c = float(t[0].item()), float(t[1].item())
+        h2d = N * wl.act_dim * 4
+        res["e2e"] = {
+            "value": N * world * e2e_steps / (ms_e * 1e-3), "unit": UNIT, "steps": e2e_steps,
+            "ms_per_step": ms_e / e2e_steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "api": ("rs_vss_env_step_host" if wl.task == "vss" else "rs_ssl_env_step_host") +
+                   " (pinned host buffers: actions read over PCIe by the kernel, one packed D2H of obs/reward/done/trunc, sync)",
+            "pcie_gbs": (h2d + d2h) / (ms_e * 1e-3 / e2e_steps) / 1e9,
+            "d2h_ceiling_gbs": d2h / (ms_c * 1e-3 / e2e_steps) / 1e9,
+            "d2h_ceiling_what": "plain cudaMemcpyAsync of the same %d-byte block + sync, %d rank(s) at once: the box's own "
+                                "limit for this transfer" % (d2h, world),
+            "frac_of_ceiling": (ms_c / ms_e),
+        }
+    del graph
+    return res
+
+
+def summarise(wl, res, K, W, world, peak, peak_src):
+    per_launch_s = res["ms_per_step"] * 1e-3
+    achieved = wl.cfg["alg"] * wl.N / per_launch_s / 1e9
+    d = {
+        "workload": wl.cfg["workload"], "envs_per_gpu": wl.N, "value": wl.N * world / per_launch_s, "unit": UNIT,
+        "ms_per_step": res["ms_per_step"], "steps": K, "repeats": res["repeats"], "warmup": W,
+        "graph_len": res["graph_len"], "worlds_rotated": wl.M, "settle_steps": wl.cfg["settle"] * wl.M,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "alg_bytes_per_env_step": wl.cfg["alg"], "alg_bytes_per_launch": wl.cfg["alg"] * wl.N,
+                     "avg_launch_us": per_launch_s * 1e6, "kernel": wl.kernel, "peak_source": peak_src},
+    }
+    if "e2e" in res:
+        d["e2e"] = res["e2e"]
+    return d
+
+
+def gather_bench(torch, dist, wl, stream, dev, world, T=8):
+    """the one collective of the design -- the all-gather that concatenates rollout
+    tensors -- alone, and on a side stream while the next rollout runs (rsoccer_b200.sharding)."""
+    from rsoccer_b200.sharding import gather_rollout
+    N, D = wl.N, wl.obs_dim
+    traj = torch.empty(T, N, D, dtype=torch.float32, device=dev)
+    side = torch.cuda.Stream(device=dev)
+
+    def rollout():
+        for i in range(T):
+            wl.step(i)
+            traj[i].copy_(wl.outs[i % wl.M][0])
+
+    def timed(fn, reps=5):
+        fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.cuda.stream(stream):
+        ms_roll = timed(rollout)
+        ms_gath = timed(lambda: gather_rollout(traj, n_total=N * world, dim=1))
+
+        # the next rollout overwrites traj while the gather reads it: double-buffer as a consumer would
+        traj2 = traj.clone()
+
+        def both_db():
+            out, ev = gather_rollout(traj2, n_total=N * world, dim=1, stream=side)
+            rollout()
+            stream.wait_event(ev)
+            return out
+        ms_both = timed(both_db)
+    recv = T * N * D * 4 * world
+    return {"what": "all_gather_into_tensor of obs[T=%d, %d, %d] f32 per rank over NCCL (rsoccer_b200.sharding.gather_rollout)" % (T, N, D),
+            "bytes_out_per_rank": recv, "ms_gather": ms_gath, "algbw_gbs": recv / (ms_gath * 1e-3) / 1e9,
+            "busbw_gbs": recv * (world - 1) / world / (ms_gath * 1e-3) / 1e9,
+            "ms_rollout_alone": ms_roll, "ms_rollout_with_gather_on_side_stream": ms_both,
+            "overlap_hidden_frac": max(0.0, min(1.0, (ms_roll + ms_gath - ms_both) / ms_gath))}
+
+
 def main():
     out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24000, help="timed steps (default = 20 episode horizons)")
-    ap.add_argument("--warmup", type=int, default=4800)
-    ap.add_argument("--min-warmup", type=int, default=600,
-                    help="lower bound on untimed steps PER WORLD (half an episode horizon), so that the timed\n"
-                         "region sees the steady-state contact density (robots on walls) and boosted clocks,\n"
-                         "not freshly reset scenes (which step ~25 %% faster)")
+    ap.add_argument("--steps", type=int, default=240, help="K: steps per timed group (one CUDA graph holds a multiple of K)")
+    ap.add_argument("--warmup", type=int, default=8, help="W: direct launches right before the timed region (>= 3)")
+    ap.add_argument("--min-ms", type=float, default=60.0, help="the timed region replays the graph until it holds this much device time")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
-    ap.add_argument("--worlds", type=int, default=8, help="independent worlds rotated through (L2)")
+    ap.add_argument("--config", default="vss65536", choices=sorted(CONFIGS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU of the main config")
+    ap.add_argument("--overlap", type=int, default=int(os.environ.get("RS_BENCH_OVERLAP", "1")), choices=[0, 1, 2],
+                    help="RS_OPT_STEP_OVERLAP of the timed worlds (include/rsoccer_b200.h)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="main config only: no configs / strong / gather / serialized sub-records")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,7 +587,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world, out)
+        run_reference(args, rank, out)
         return
 
     import torch
@@ -204,133 +598,97 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    placement = bind_near_gpu(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    N, M = args.envs, max(1, args.worlds)
-    W = max(3, args.warmup, args.min_warmup * M)
-    K = max(1, args.steps)
-    worlds, acts, outs = [], [], []
-    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    for m in range(M):
-        w = E.BatchedWorld(E.KIND_VSS, 0, 3, 3, 25, N, device=dev, seed=2024,
-                           env_offset=(rank * M + m) * N)
-        w.task_reset(E.TASK_VSS_V0)
-        worlds.append(w)
-        acts.append((torch.rand(N, 2, generator=gen) * 2 - 1).to(dev))
-        outs.append(w.alloc_outputs(E.TASK_VSS_V0))
-    torch.cuda.synchronize()
-    launches0 = sum(w.launches for w in worlds)
-
-    def step(i):
-        m = i % M
-        worlds[m].vss_env_step(acts[m], out=outs[m])
-
+    K, W = max(1, args.steps), max(3, args.warmup)
+    peak, peak_src = _peaks()
     stream = torch.cuda.Stream(device=dev)
-    graph = None
-    with torch.cuda.stream(stream):
-        for i in range(W):
-            step(i)
-        stream.synchronize()
-        if not args.no_graph:
-            # one graph = G = 4 passes over the M worlds (-1 % vs one pass per graph launch)
-            G = 4 * M
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream):
-                for i in range(G):
-                    step(i)
-            graph.replay()
-            stream.synchronize()
-    G = 4 * M
-    reps, tail = (K // G, K % G) if graph is not None else (0, K)     # EXACTLY K steps are timed
+    cfg = dict(CONFIGS[args.config])
+    envs = args.envs or cfg["envs"] or max(1, 65536 // world)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(reps):
-            graph.replay()
-        for i in range(tail):
-            step(i)
-        ev1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    launches = reps * G + tail
-    value = N * world * K / (ms * 1e-3)
+    wl = Workload(torch, E, args.config, cfg, envs, dev, rank, args.overlap, K)
+    launches0 = sum(w.launches for w in wl.worlds)
+    res = measure(torch, dist, wl, K, W, args.min_ms, stream, world, dev, e2e_steps=max(10, args.e2e_steps),
+                  clock_index=local_rank)
+    main_sum = summarise(wl, res, K, W, world, peak, peak_src)
+    launches_timed = res["steps_timed"]
+    extras = {}
+    if not args.no_extras:
+        # the same worlds with the grid-wide wait between steps (RS_OPT_STEP_OVERLAP = 0), for the record
+        if args.overlap != 0:
+            wl.set_overlap(0)
+            r0 = measure(torch, dist, wl, K, W, args.min_ms / 2, stream, world, dev, settle=False, e2e_steps=0)
+            extras["serialized"] = {"ms_per_step": r0["ms_per_step"], "value": envs * world / (r0["ms_per_step"] * 1e-3),
+                                    "frac": cfg["alg"] * envs / (r0["ms_per_step"] * 1e-3) / 1e9 / peak,
+                                    "what": "same graph with RS_OPT_STEP_OVERLAP = 0: every step waits for the whole previous grid"}
+            wl.set_overlap(args.overlap)
+        if world > 1 and cfg["task"] == "vss":
+            extras["gather"] = gather_bench(torch, dist, wl, stream, dev, world)
+    wl.close()
+    del wl
+    torch.cuda.empty_cache()
 
-    # ---- e2e: the public host-buffer call, pinned host memory, H2D + D2H inside the timing
-    Ke = max(10, args.e2e_steps)
-    w0 = worlds[0]
-    h_act = torch.empty(N, 2, dtype=torch.float32).pin_memory()
-    h_act.copy_(acts[0].cpu())
-    h_obs, h_rew, h_done, h_trunc = w0.alloc_host_outputs(E.TASK_VSS_V0)   # one pinned block -> one D2H copy
-    with torch.cuda.stream(stream):
-        for _ in range(3):
-            w0.vss_env_step_host(h_act, h_obs, h_rew, h_done, h_trunc)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(Ke):
-            w0.vss_env_step_host(h_act, h_obs, h_rew, h_done, h_trunc)
-        e1.record(stream)
-        torch.cuda.synchronize()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e_value = N * world * Ke / (ms_e2e * 1e-3)
+    if not args.no_extras:
+        subs = {}
+        names = [n for n in ("vss4096", "sd4096", "cp16384", "vss262144_sharded") if n != args.config]
+        for name in names:
+            c = dict(CONFIGS[name])
+            w2 = Workload(torch, E, name, c, c["envs"], dev, rank, args.overlap, K, seed_base=1 + names.index(name))
+            r2 = measure(torch, dist, w2, K, W, args.min_ms / 2, stream, world, dev, e2e_steps=30)
+            subs[name] = summarise(w2, r2, K, W, world, peak, peak_src)
+            w2.close()
+            del w2
+            torch.cuda.empty_cache()
+        extras["configs"] = subs
+        if args.config != "vss65536_strong":
+            c = dict(CONFIGS["vss65536_strong"])
+            n_s = max(1, 65536 // world)
+            w3 = Workload(torch, E, "vss65536_strong", c, n_s, dev, rank, args.overlap, K, seed_base=7)
+            r3 = measure(torch, dist, w3, K, W, args.min_ms / 2, stream, world, dev, e2e_steps=30)
+            extras["strong"] = summarise(w3, r3, K, W, world, peak, peak_src)
+            extras["strong"]["scaling"] = "strong"
+            extras["strong"]["envs_total"] = n_s * world
+            w3.close()
+            del w3
 
     if rank == 0:
-        peak, peak_src = _peaks()
-        per_launch_s = ms * 1e-3 / K
-        achieved = ALG_BYTES_PER_ENV_STEP * N / per_launch_s / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("k_vss_env_step_dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic = tj.get("k_vss_env_step_dram_bytes_per_launch") if cfg["task"] == "vss" and envs == 65536 else None
+            traffic_src = tj.get("source")
         except Exception:
             pass
-        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        cpu = cpu_baseline_run(ncpu, args.cpu_seconds)
+        cpu = cpu_baseline_run(cfg["task"], _host_threads(), args.cpu_seconds)
+        modes = {0: "every step begins with a grid-wide wait on its predecessor (programmatic dependent launch hides the launch latency only)",
+                 1: "RS_OPT_STEP_OVERLAP=1: steps synchronise per 32-match tile on the world state and grid-wide before reading the action buffer",
+                 2: "RS_OPT_STEP_OVERLAP=2: steps synchronise per 32-match tile only (fixed action buffers)"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "VSS-v0 3v3, %d envs per GPU" % N, "envs_per_gpu": N,
-                       "field_type": 0, "time_step_ms": 25, "substeps": 5,
+            "metric": METRIC, "value": main_sum["value"], "unit": UNIT, "n_gpus": world, "steps": K,
+            "repeats": main_sum["repeats"], "warmup": W, "ms_per_step": main_sum["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong" if args.config == "vss65536_strong" else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "envs_per_gpu": envs, "field_type": 0 if cfg["task"] == "vss" else 2,
+                       "time_step_ms": 25, "substeps": 5,
                        "l2": "inputs larger than L2: %d independent %d-env worlds rotated (%.0f MB per pass > 126 MB L2)"
-                             % (M, N, M * N * ALG_BYTES_PER_ENV_STEP / 1e6),
-                       "launch": ("cuda graph replay" if graph is not None else "direct launches")
-                                 + ", programmatic dependent launch between consecutive steps",
-                       "parallelism": "env-sharded x%d, no collective on the step path" % world},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "steps": Ke, "ms_per_step": ms_e2e / Ke,
-                    "h2d_bytes_per_step": N * 2 * 4, "d2h_bytes_per_step": N * (40 * 4 + 4 + 1 + 1),
-                    "api": "rs_vss_env_step_host (pinned host buffers: actions read over PCIe by the kernel, one packed D2H of obs/reward/done/trunc, sync)",
-                    "pcie_gbs": (N * 2 * 4 + N * (40 * 4 + 4 + 1 + 1)) / (ms_e2e * 1e-3 / Ke) / 1e9},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_vss_env_step<3,3,64,2> (VssF0P: compile-time constants, packed fp32x2 forms)",
-                         "alg_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * N,
-                         "avg_launch_us": per_launch_s * 1e6},
+                             % (main_sum["worlds_rotated"], envs, main_sum["worlds_rotated"] * envs * cfg["alg"] / 1e6),
+                       "launch": "CUDA graph of %d steps (%d x K) replayed %d times = %d timed launches; %s"
+                                 % (res["graph_len"], res["graph_len"] // K, res["replays"], res["steps_timed"], modes[args.overlap]),
+                       "settle_steps": main_sum["settle_steps"],
+                       "timed_region_ms": res["ms_total"],
+                       "parallelism": "env-sharded x%d, no collective on the step path" % world,
+                       "host_placement": placement},
+            "clocks": res.get("clocks"),
+            "e2e": res["e2e"],
+            "gpu_launches": launches_timed,
+            "roofline": dict(main_sum["roofline"], traffic=traffic,
+                             traffic_source=traffic_src if traffic is not None else None),
             "cpu_baseline": cpu,
         }
+        line.update(extras)
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()

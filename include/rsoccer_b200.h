@@ -32,7 +32,11 @@
  *    never retains a caller pointer past the call, except the state buffer given
  *    to rs_bind_state, which the caller keeps alive until rs_destroy.
  *  - calls are asynchronous on `stream` unless stated; a handle is not thread
- *    safe; there is no global state besides the per-thread error string.
+ *    safe (one caller at a time; handles are independent of each other); there is
+ *    no global state besides the per-thread error string -- every tuning switch is
+ *    per handle, and the process environment is read once, in rs_create.
+ *  - every call runs on the world's own CUDA device (rs_create's `device`) whatever
+ *    device is current in the calling thread, and restores the caller's device.
  *  - return 0 on success, <0 on error (RS_E_*); rs_last_error() has the text.
  *  - there is NO CPU fallback: rs_create fails if no CUDA device is usable.
  *  - units on the wire follow the reference (Entities/Frame.py:8): m, m/s,
@@ -114,13 +118,40 @@ int rs_get_state(const rs_world *w, float *d_out, void *stream);
 int rs_set_raw(rs_world *w, const float *d_in, void *stream);
 int rs_get_raw(const rs_world *w, float *d_out, void *stream);
 
-/* world step counter (Philox counter word 1); incremented by every step call */
+/* World step counter t = Philox counter word 1: 32 bits, wraps modulo 2^32 (rs_set_t rejects
+ * larger values).  It is advanced ON THE DEVICE by every task-level step (rs_vss_env_step,
+ * rs_ssl_env_step) -- so a captured CUDA graph replays with fresh noise -- and by nothing else:
+ * rs_step draws no random numbers and leaves it alone.  rs_get_t returns the host mirror,
+ * exact unless launches were replayed from a graph; rs_sync_t (blocking) reads the device
+ * value back, or, if an rs_set_t is still pending, writes it.  A pending rs_set_t is applied
+ * by the next step launch; that launch fails with RS_E_STATE inside a stream capture (the
+ * write would be replayed with the graph and rewind the counter). */
 uint64_t rs_get_t(const rs_world *w);
 int rs_set_t(rs_world *w, uint64_t t);
-/* The counter the kernels read lives in device memory (so a captured CUDA graph replays
- * with fresh Philox counters); rs_get_t returns the host mirror, which is exact unless
- * launches were replayed from a graph -- rs_sync_t reads the device value back (blocking). */
 int rs_sync_t(rs_world *w, void *stream);
+
+/* ---- per-handle options ---- */
+/* RS_OPT_STEP_OVERLAP (default 0; rs_create reads RS_STEP_OVERLAP from the environment):
+ * consecutive rs_vss_env_step launches of one world on one stream synchronise per 32-match
+ * tile instead of grid-wide, so that the tail of step k (slow tiles, store drain) overlaps the
+ * head of step k+1 (launch, state loads, noise).  Results are bit-identical to mode 0.
+ *   0  off: every step begins with a grid-wide wait on the previous kernel of the stream.
+ *   1  the world state is synchronised per tile; caller buffers (d_actions, d_normals) are
+ *      read only after a grid-wide wait.  Always safe.
+ *   2  per tile only, no grid-wide wait at all.  The caller vouches that d_actions /
+ *      d_normals were completely written before the PREVIOUS step launch of this world was
+ *      enqueued (fixed or pre-generated action buffers, action repeat).  Any other work
+ *      enqueued between two steps (a policy kernel, a copy) serialises them as usual.
+ * Whoever writes the state buffer behind the library's back (through the zero-copy views)
+ * sets the option again afterwards: the next step then starts with a grid-wide wait.
+ * RS_OPT_PDL (default 1): launch step kernels with programmatic stream serialization.
+ * RS_OPT_OVERLAP_ERRORS (read only, blocking): tiles whose wait timed out -- always 0 unless
+ * one world was stepped from two streams at once. */
+#define RS_OPT_STEP_OVERLAP 1
+#define RS_OPT_PDL 2
+#define RS_OPT_OVERLAP_ERRORS 3
+int rs_set_option(rs_world *w, int option, int64_t value);
+int rs_get_option(const rs_world *w, int option, int64_t *value, void *stream);
 
 /* ---- task level: the env.step() of the benchmarked reference envs ---- */
 #define RS_TASK_VSS_V0 0
@@ -167,7 +198,8 @@ int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto
                          int max_steps, float *h_obs, float *h_reward, uint8_t *h_done,
                          uint8_t *h_trunc, void *stream);
 
-/* number of kernels this handle has launched so far (bench.py gpu_launches) */
+/* number of kernels this handle has launched so far (bench.py gpu_launches); atomic, so
+ * the const getters above may run concurrently with each other */
 uint64_t rs_launch_count(const rs_world *w);
 
 /* which kernels step this world (diagnostics; the results do not depend on it):

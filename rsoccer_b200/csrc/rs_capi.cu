@@ -3,6 +3,7 @@
 // Build (see __graft_entry__.build):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 //        -o rsoccer_b200/librsoccer_b200.so rsoccer_b200/csrc/rs_capi.cu
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,9 +38,12 @@ struct VssStepArgs {
     uint64_t seed;
     uint32_t *ctr;           // world step counter t (Philox counter word 1), one copy per RS_CTR_GROUP matches
     uint32_t env_offset;
-#ifdef RS_X_STAGGER
-    int stagger_ns, stagger_mode;   // experiment: delay half of the CTAs (RS_STAGGER_NS, RS_STAGGER_MODE)
-#endif
+    // step-to-step overlap (rs_device.cuh, tile_acquire): one flag word per 32-match tile + one error
+    // word behind them, or null.  chain = 0: grid-wide wait first (griddepcontrol.wait), 1: per-tile wait
+    // for the state, grid-wide wait before the first read of a caller buffer (actions, normals),
+    // 2: per-tile wait only (the caller vouches for its buffers, RS_OPT_STEP_OVERLAP = 2)
+    uint32_t *flags;
+    int chain;
 };
 
 // VSSEnv.step for BS matches per CTA, one lane per match.  ONE launch = commands (agent +
@@ -63,23 +67,18 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
-    pdl_wait();
+    uint32_t *const tile_flag = A.flags ? A.flags + (w0 >> 5) : nullptr;
+    if (A.chain == 0) pdl_wait();
+    if (tile_flag) tile_acquire(tile_flag, A.flags + ((S.np + 31) >> 5));
     pdl_release();
-#ifdef RS_X_STAGGER
-    if (A.stagger_ns > 0) {
-        const unsigned k = blockIdx.x / 148u;
-        const bool late = A.stagger_mode == 0 ? (k & 2u) != 0u : A.stagger_mode == 1 ? (k & 1u) != 0u : (blockIdx.x & 1u) != 0u;
-        if (late) __nanosleep((unsigned)A.stagger_ns);
-    }
-#endif
     if (e < S.n) {
         // ---- every global load of the step is issued first: the step counter ahead of the state,
         // so that it is not queued behind 100 KB of requests per SM and Philox can start at once
         const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
         Scene<R> s;
         load_scene<R>(P, S, e, s);
-        const int st = S.steps[e];
-        float prev = S.prev[e];
+        const int st = __ldcg(S.steps + e);
+        float prev = __ldcg(S.prev + e);
         // reward_shaping_total is never loaded: the six accumulators are zeroed by a store at the
         // first step of an episode and updated by fire-and-forget reductions (RED.ADD.F32, one
         // add per word and step: same rounding as load-add-store) -- move / ball_grad / energy every
@@ -87,13 +86,15 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         // bytes a step used to move per env.
         float2 ou[R - 1];
 #pragma unroll
-        for (int r = 1; r < R; ++r) ou[r - 1] = S.ou[(size_t)(r - 1) * S.np + e];
-        const float2 act = A.actions[e];
+        for (int r = 1; r < R; ++r) ou[r - 1] = __ldcg(S.ou + (size_t)(r - 1) * S.np + e);
+        float2 act = make_float2(0.0f, 0.0f);
+        if (A.chain != 1) act = A.actions[e];
 
         // ---- ... and the OU noise (Philox + Box-Muller, ~15 % of the instructions, needs
         // only the env id and the step counter) is computed while they are in flight
         float z[NZ];
         if (A.normals) {
+            if (A.chain == 1) pdl_wait();
 #pragma unroll
             for (int k = 0; k < NZ; ++k) z[k] = A.normals[(size_t)e * NZ + k];
         } else {
@@ -113,6 +114,10 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
                 if (4 * j + 3 < NZ) z[4 * j + 3] = -rr * sn;
             }
         }
+
+        // caller buffers are read only after the predecessor grid has completed (chain 1: the state
+        // loads and the noise above already ran under its tail)
+        if (A.chain == 1) { pdl_wait(); act = A.actions[e]; }
 
         // ---- _get_commands, vss_gym.py:119-142
         Drive<R> d;
@@ -214,6 +219,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 #pragma unroll
         for (int i = 0; i < NOBS / 4; ++i) { const int k = i * 32 + (tid & 31); if (k < total) dst[k] = src[k]; }
     }
+    if (tile_flag) tile_release(tile_flag);
 }
 
 
@@ -1004,11 +1010,11 @@ struct rs_world {
     int n, np, device;
     uint64_t seed;
     int64_t env_offset;
-    uint64_t t;              // host mirror of d_ctr[0]
-    bool t_dirty;            // host t changed without the device counter (rs_step, rs_set_t)
+    uint64_t t;              // host mirror of the device step counter (exact unless launches were replayed from a graph)
+    bool t_dirty;            // rs_set_t changed the host value; the next step launch writes it to the device
     uint32_t *d_ctr;         // device: t, one copy per RS_CTR_GROUP matches (library-owned)
     int n_ctr;
-    uint64_t launches;
+    mutable std::atomic<uint64_t> launches;   // counted by const getters too: no const_cast, no torn counts
     void *state;
     int64_t off[RS_ARR_COUNT];
     size_t state_bytes;
@@ -1017,11 +1023,36 @@ struct rs_world {
     int per_match;           // 1: one lane per MATCH kernels (rs_device.cuh); 0: one lane per BODY (rs_lanes.cuh); -1: by world size
     int lane_block;          // CTA size of the lane-per-body kernels
     int packed;              // 1: packed fp32x2 instruction forms in the VssF0 kernels; 0: scalar forms; -1: by world size
+    bool pdl;                // step kernels are launched with programmatic stream serialization (RS_PDL=0 turns it off)
+    bool host_copy_actions;  // RS_HOST_COPY_ACTIONS=1: stage pinned host actions with a copy instead of reading them in place
+    // step-to-step overlap (RS_OPT_STEP_OVERLAP; rs_device.cuh, tile_acquire)
+    int overlap;             // 0 off, 1 state through tile flags + grid wait before caller buffers, 2 tile flags only
+    uint32_t *d_flags;       // [np / 32] tile flags + 1 error word (library-owned)
+    bool chain_ok;           // the previous launch that touched the state was a flag-protocol step ...
+    cudaStream_t chain_stream;   // ... on this stream
     // scratch for the *_host entry points (library owned)
     float *s_actions, *s_obs, *s_reward;
     uint8_t *s_done, *s_trunc;
     int s_act_dim, s_obs_dim;
+    const void *h_act_seen;  // last host action pointer looked up with cudaPointerGetAttributes ...
+    const float *h_act_dev;  // ... and its device alias (null: pageable, staged with a copy)
 };
+
+// Every entry point that launches or allocates runs on the world's own device, whatever device is
+// current in the calling thread, and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(true) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) { ok = false; return; }
+        if (cur != dev) { ok = cudaSetDevice(dev) == cudaSuccess; if (ok) prev = cur; }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(w, name)                                                                  \
+    DeviceGuard _dg((w)->device);                                                           \
+    if (!_dg.ok) return fail(RS_E_CUDA, name ": cannot select the world's CUDA device")
 
 static void fill_dev_params(const rs_params &p, DevParams &d) {
     memset(&d, 0, sizeof(d));
@@ -1128,41 +1159,52 @@ static bool use_packed(const rs_world *w) {
 
 // Launch of a step kernel, by default with programmatic stream serialization (PDL): the
 // kernel's pre-wait part overlaps the tail of its predecessor in the stream (rs_device.cuh).
-static bool g_pdl = true;
+// The first failing launch of a call is kept in the world-independent, per-thread g_launch_err
+// and turned into RS_E_CUDA by the entry point (LAUNCH_CHECK).
+static thread_local cudaError_t g_launch_err = cudaSuccess;
 template <typename... KArgs, typename... Args>
-static void launch_step_kernel(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+static void launch_step_kernel(const rs_world *w, void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1u : 0u;
-    cudaLaunchKernelEx(&cfg, kernel, args...);
+    cfg.attrs = at; cfg.numAttrs = w->pdl ? 1u : 0u;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
+    w->launches++;
 }
+#define LAUNCH_CHECK(name)                                                                  \
+    do {                                                                                    \
+        cudaError_t _e = g_launch_err;                                                      \
+        g_launch_err = cudaSuccess;                                                         \
+        if (_e == cudaSuccess) _e = cudaGetLastError();                                     \
+        if (_e != cudaSuccess) return fail(RS_E_CUDA, std::string(name ": kernel launch failed: ") + cudaGetErrorString(_e)); \
+    } while (0)
 
 template <int KIND, int RT>
 static void launch_step(rs_world *w, const float *cmds, cudaStream_t st) {
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
     if constexpr (KIND == RS_KIND_VSS && RT == VssF0::n_robots) {
         if (w->f0) {            // rs_create compared the constants bit for bit (matches_vss_f0)
-            if (use_packed(w)) launch_step_kernel(k_step<KIND, RT, 64, 2>, g64, 64, st, w->dp, state_ptrs(w), cmds);
-            else launch_step_kernel(k_step<KIND, RT, 64, 1>, g64, 64, st, w->dp, state_ptrs(w), cmds);
+            if (use_packed(w)) launch_step_kernel(w, k_step<KIND, RT, 64, 2>, g64, 64, st, w->dp, state_ptrs(w), cmds);
+            else launch_step_kernel(w, k_step<KIND, RT, 64, 1>, g64, 64, st, w->dp, state_ptrs(w), cmds);
             return;
         }
     }
-    if (w->block == 128) launch_step_kernel(k_step<KIND, RT, 128>, g128, 128, st, w->dp, state_ptrs(w), cmds);
-    else launch_step_kernel(k_step<KIND, RT, 64>, g64, 64, st, w->dp, state_ptrs(w), cmds);
+    if (w->block == 128) launch_step_kernel(w, k_step<KIND, RT, 128>, g128, 128, st, w->dp, state_ptrs(w), cmds);
+    else launch_step_kernel(w, k_step<KIND, RT, 64>, g64, 64, st, w->dp, state_ptrs(w), cmds);
 }
 
 // lane-per-body launches: grid = matches / (BS / L)
 template <int KIND, int L>
 static void launch_step_lanes_l(rs_world *w, const float *cmds, cudaStream_t st) {
     const StatePtrs S = state_ptrs(w);
-    if (w->lane_block == 256) launch_step_kernel(k_step_lanes<KIND, L, 256>, (w->n + 256 / L - 1) / (256 / L), 256, st, w->dp, S, cmds);
-    else if (w->lane_block == 64) launch_step_kernel(k_step_lanes<KIND, L, 64>, (w->n + 64 / L - 1) / (64 / L), 64, st, w->dp, S, cmds);
-    else if (KIND == RS_KIND_VSS && L == 8 && w->f0) launch_step_kernel(k_step_lanes<RS_KIND_VSS, 8, 128, true>, (w->n + 15) / 16, 128, st, w->dp, S, cmds);
-    else launch_step_kernel(k_step_lanes<KIND, L, 128>, (w->n + 128 / L - 1) / (128 / L), 128, st, w->dp, S, cmds);
+    if (w->lane_block == 256) launch_step_kernel(w, k_step_lanes<KIND, L, 256>, (w->n + 256 / L - 1) / (256 / L), 256, st, w->dp, S, cmds);
+    else if (w->lane_block == 64) launch_step_kernel(w, k_step_lanes<KIND, L, 64>, (w->n + 64 / L - 1) / (64 / L), 64, st, w->dp, S, cmds);
+    else if (KIND == RS_KIND_VSS && L == 8 && w->f0) launch_step_kernel(w, k_step_lanes<RS_KIND_VSS, 8, 128, true>, (w->n + 15) / 16, 128, st, w->dp, S, cmds);
+    else launch_step_kernel(w, k_step_lanes<KIND, L, 128>, (w->n + 128 / L - 1) / (128 / L), 128, st, w->dp, S, cmds);
 }
 template <int KIND>
 static void launch_step_lanes(rs_world *w, const float *cmds, cudaStream_t st) {
@@ -1176,7 +1218,7 @@ static void launch_step_lanes(rs_world *w, const float *cmds, cudaStream_t st) {
 
 extern "C" {
 
-int rs_version(void) { return 100; }
+int rs_version(void) { return 200; }
 const char *rs_last_error(void) { return g_err.c_str(); }
 
 int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_ms, int n_envs,
@@ -1194,10 +1236,11 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     if (ce != cudaSuccess || count == 0)
         return fail(RS_E_CUDA, std::string("rs_create: no CUDA device (there is no CPU fallback): ") +
                                    cudaGetErrorString(ce));
-    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
-    else CUDA_TRY(cudaGetDevice(&device));
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));      // "the current device", resolved once, here
+    if (device >= count) return fail(RS_E_INVALID, "rs_create: no such CUDA device");
+    DeviceGuard dg(device);                                // the caller's current device is left alone
+    if (!dg.ok) return fail(RS_E_CUDA, "rs_create: cannot select the CUDA device");
     rs_world *w = new rs_world();
-    memset(w, 0, sizeof(*w));
     w->p = p; fill_dev_params(p, w->dp);
     w->n = n_envs; w->np = (n_envs + 127) / 128 * 128; w->device = device;
     w->seed = seed; w->env_offset = env_offset; w->t = 0;
@@ -1211,20 +1254,30 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     w->off[RS_ARR_STEPS] = (int64_t)o; o += 4 * np;
     w->off[RS_ARR_INFO] = (int64_t)o; o += 4 * (size_t)RS_SSL_INFO * np;
     w->state_bytes = o;
+    // the environment is read here, once per handle, never on a step
     w->block = 64;
     w->per_match = -1; w->lane_block = 128;
     if (const char *ls = getenv("RS_PER_MATCH")) w->per_match = atoi(ls) != 0;
     w->packed = -1;
     if (const char *ls = getenv("RS_PACKED")) w->packed = atoi(ls) != 0;
-    if (const char *ls = getenv("RS_PDL")) g_pdl = atoi(ls) != 0;
+    w->pdl = true;
+    if (const char *ls = getenv("RS_PDL")) w->pdl = atoi(ls) != 0;
+    w->host_copy_actions = false;
+    if (const char *ls = getenv("RS_HOST_COPY_ACTIONS")) w->host_copy_actions = atoi(ls) != 0;
     if (const char *bs = getenv("RS_LANE_BLOCK")) { const int b = atoi(bs); if (b == 64 || b == 128 || b == 256) w->lane_block = b; }
     w->f0 = matches_vss_f0(w->dp) ? 1 : 0;
     if (const char *nv = getenv("RS_NO_PRESET")) { if (atoi(nv) == 1) w->f0 = 0; }
     if (const char *bs = getenv("RS_BLOCK")) { const int b = atoi(bs); if (b == 32 || b == 64 || b == 128 || b == 256) w->block = b; }
+    w->overlap = 0;
+    if (const char *ov = getenv("RS_STEP_OVERLAP")) { const int v = atoi(ov); if (v >= 0 && v <= 2) w->overlap = v; }
     w->n_ctr = w->np / RS_CTR_GROUP;
-    if (cudaMalloc(&w->d_ctr, w->n_ctr * sizeof(uint32_t)) != cudaSuccess || cudaMemset(w->d_ctr, 0, w->n_ctr * sizeof(uint32_t)) != cudaSuccess) {
+    const size_t flag_bytes = ((size_t)w->np / 32 + 1) * sizeof(uint32_t);
+    if (cudaMalloc(&w->d_ctr, w->n_ctr * sizeof(uint32_t)) != cudaSuccess || cudaMemset(w->d_ctr, 0, w->n_ctr * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&w->d_flags, flag_bytes) != cudaSuccess || cudaMemset(w->d_flags, 0, flag_bytes) != cudaSuccess) {
+        cudaFree(w->d_ctr); cudaFree(w->d_flags);
+        cudaGetLastError();
         delete w;
-        return fail(RS_E_CUDA, "rs_create: cudaMalloc of the step counter failed");
+        return fail(RS_E_CUDA, "rs_create: cudaMalloc of the step counter / tile flags failed");
     }
     *out = w;
     return RS_OK;
@@ -1232,8 +1285,11 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
 
 int rs_destroy(rs_world *w) {
     if (!w) return RS_OK;
-    cudaFree(w->s_actions); cudaFree(w->s_obs);      // s_reward / s_done / s_trunc live inside s_obs's allocation
-    cudaFree(w->d_ctr);
+    {
+        DeviceGuard dg(w->device);
+        cudaFree(w->s_actions); cudaFree(w->s_obs);      // s_reward / s_done / s_trunc live inside s_obs's allocation
+        cudaFree(w->d_ctr); cudaFree(w->d_flags);
+    }
     delete w;
     return RS_OK;
 }
@@ -1250,8 +1306,10 @@ int rs_layout(const rs_world *w, int64_t *out_offsets, int64_t *out_np) {
 int rs_bind_state(rs_world *w, void *d_state, void *stream) {
     if (!w || !d_state) return fail(RS_E_INVALID, "rs_bind_state: null argument");
     if ((uintptr_t)d_state & 255u) return fail(RS_E_INVALID, "rs_bind_state: buffer must be 256-byte aligned");
+    ON_DEVICE(w, "rs_bind_state");
     cudaStream_t st = (cudaStream_t)stream;
     w->state = d_state;
+    w->chain_ok = false;
     CUDA_TRY(cudaMemsetAsync(d_state, 0, w->state_bytes, st));
     k_init<<<(w->n + 127) / 128, 128, 0, st>>>(w->dp, state_ptrs(w));
     w->launches++;
@@ -1267,24 +1325,28 @@ int rs_field_params(const rs_world *w, double out[17]) {
 
 #define NEED_STATE(w, name)                                                                 \
     if (!(w)) return fail(RS_E_INVALID, name ": null world");                               \
-    if (!(w)->state) return fail(RS_E_STATE, name ": no state buffer bound (rs_bind_state)")
+    if (!(w)->state) return fail(RS_E_STATE, name ": no state buffer bound (rs_bind_state)"); \
+    ON_DEVICE(w, name)
 
 int rs_reset(rs_world *w, const float *d_ball, const float *d_blue, const float *d_yellow,
              const uint8_t *d_mask, void *stream) {
     NEED_STATE(w, "rs_reset");
     if (!d_ball || (w->p.n_blue && !d_blue) || (w->p.n_yellow && !d_yellow))
         return fail(RS_E_INVALID, "rs_reset: null placement array");
+    w->chain_ok = false;
     k_reset<<<(w->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dp, state_ptrs(w), d_ball, d_blue, d_yellow, d_mask);
     w->launches++;
     CUDA_TRY(cudaGetLastError());
     return RS_OK;
 }
 
+// robosim.step: pure physics, no random numbers -- the Philox step counter is not touched
 int rs_step(rs_world *w, const float *d_cmds, void *stream) {
     NEED_STATE(w, "rs_step");
     if (!d_cmds) return fail(RS_E_INVALID, "rs_step: null commands");
     cudaStream_t st = (cudaStream_t)stream;
     const int R = w->p.n_robots;
+    w->chain_ok = false;
     if (use_lane_per_body(w, false)) {
         if (w->p.kind == RS_KIND_VSS) launch_step_lanes<RS_KIND_VSS>(w, d_cmds, st);
         else launch_step_lanes<RS_KIND_SSL>(w, d_cmds, st);
@@ -1300,8 +1362,7 @@ int rs_step(rs_world *w, const float *d_cmds, void *stream) {
         else if (R == 1) launch_step<RS_KIND_SSL, 1>(w, d_cmds, st);
         else launch_step<RS_KIND_SSL, 0>(w, d_cmds, st);
     }
-    w->launches++; w->t++; w->t_dirty = true;
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH_CHECK("rs_step");
     return RS_OK;
 }
 
@@ -1309,7 +1370,7 @@ int rs_get_state(const rs_world *w, float *d_out, void *stream) {
     NEED_STATE(w, "rs_get_state");
     if (!d_out) return fail(RS_E_INVALID, "rs_get_state: null output");
     k_get_state<<<(w->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dp, state_ptrs(w), d_out);
-    const_cast<rs_world *>(w)->launches++;
+    w->launches++;
     CUDA_TRY(cudaGetLastError());
     return RS_OK;
 }
@@ -1317,6 +1378,7 @@ int rs_get_state(const rs_world *w, float *d_out, void *stream) {
 int rs_set_raw(rs_world *w, const float *d_in, void *stream) {
     NEED_STATE(w, "rs_set_raw");
     if (!d_in) return fail(RS_E_INVALID, "rs_set_raw: null input");
+    w->chain_ok = false;
     k_set_raw<<<(w->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dp, state_ptrs(w), d_in);
     w->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1326,27 +1388,51 @@ int rs_get_raw(const rs_world *w, float *d_out, void *stream) {
     NEED_STATE(w, "rs_get_raw");
     if (!d_out) return fail(RS_E_INVALID, "rs_get_raw: null output");
     k_get_raw<<<(w->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->dp, state_ptrs(w), d_out);
-    const_cast<rs_world *>(w)->launches++;
+    w->launches++;
     CUDA_TRY(cudaGetLastError());
     return RS_OK;
 }
 
+// The step counter t (Philox counter word 1, 32 bits on the device) is DEVICE-authoritative:
+// every task step advances it on the device (so captured graphs replay with fresh noise) and
+// the host keeps a mirror that is exact as long as no launch was replayed from a graph.  Only
+// rs_set_t writes host -> device (at the next step launch), only rs_sync_t reads device -> host.
 uint64_t rs_get_t(const rs_world *w) { return w ? w->t : 0; }
 int rs_set_t(rs_world *w, uint64_t t) {
     if (!w) return fail(RS_E_INVALID, "rs_set_t: null world");
+    if (t > 0xFFFFFFFFull) return fail(RS_E_INVALID, "rs_set_t: the Philox step counter word has 32 bits");
     w->t = t; w->t_dirty = true;
+    return RS_OK;
+}
+// applies a pending rs_set_t.  Never inside a stream capture: the write would be baked into the
+// graph and every replay would rewind the counter (and repeat the noise).
+static int push_t(rs_world *w, cudaStream_t st) {
+    if (!w->t_dirty) return RS_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (cs != cudaStreamCaptureStatusNone)
+        return fail(RS_E_STATE, "rs_set_t is pending and the stream is capturing: run one step (or rs_sync_t) outside the capture first");
+    k_set_ctr<<<(w->n_ctr + 255) / 256, 256, 0, st>>>(w->d_ctr, w->n_ctr, (uint32_t)w->t);
+    w->launches++; w->t_dirty = false; w->chain_ok = false;
     return RS_OK;
 }
 int rs_sync_t(rs_world *w, void *stream) {
     if (!w) return fail(RS_E_INVALID, "rs_sync_t: null world");
-    if (w->t_dirty) return RS_OK;      // host value is the newer one
+    ON_DEVICE(w, "rs_sync_t");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (w->t_dirty) {                  // the host value is the newer one: write it, then both agree
+        const int rc = push_t(w, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return RS_OK;
+    }
     uint32_t t = 0;
-    CUDA_TRY(cudaMemcpyAsync(&t, w->d_ctr, sizeof(t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpyAsync(&t, w->d_ctr, sizeof(t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     w->t = t;
     return RS_OK;
 }
-uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches : 0; }
+uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches.load() : 0; }
 
 int rs_kernel_flags(const rs_world *w) {
     if (!w) return 0;
@@ -1354,10 +1440,36 @@ int rs_kernel_flags(const rs_world *w) {
            (w->f0 && !use_lane_per_body(w, true) && use_packed(w) ? 8 : 0);
 }
 
-static void push_t(rs_world *w, cudaStream_t st) {
-    if (!w->t_dirty) return;
-    k_set_ctr<<<(w->n_ctr + 255) / 256, 256, 0, st>>>(w->d_ctr, w->n_ctr, (uint32_t)w->t);
-    w->launches++; w->t_dirty = false;
+int rs_set_option(rs_world *w, int option, int64_t value) {
+    if (!w) return fail(RS_E_INVALID, "rs_set_option: null world");
+    switch (option) {
+        case RS_OPT_STEP_OVERLAP:
+            if (value < 0 || value > 2) return fail(RS_E_INVALID, "rs_set_option: RS_OPT_STEP_OVERLAP takes 0, 1 or 2");
+            w->overlap = (int)value; w->chain_ok = false;     // also: "the state was written behind the library's back"
+            return RS_OK;
+        case RS_OPT_PDL:
+            w->pdl = value != 0; w->chain_ok = false;
+            return RS_OK;
+        default:
+            return fail(RS_E_INVALID, "rs_set_option: unknown or read-only option");
+    }
+}
+int rs_get_option(const rs_world *w, int option, int64_t *value, void *stream) {
+    if (!w || !value) return fail(RS_E_INVALID, "rs_get_option: null argument");
+    switch (option) {
+        case RS_OPT_STEP_OVERLAP: *value = w->overlap; return RS_OK;
+        case RS_OPT_PDL: *value = w->pdl ? 1 : 0; return RS_OK;
+        case RS_OPT_OVERLAP_ERRORS: {
+            ON_DEVICE(w, "rs_get_option");
+            uint32_t e = 0;
+            CUDA_TRY(cudaMemcpyAsync(&e, w->d_flags + w->np / 32, sizeof(e), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+            CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+            *value = e;
+            return RS_OK;
+        }
+        default:
+            return fail(RS_E_INVALID, "rs_get_option: unknown option");
+    }
 }
 
 static bool task_matches(const rs_world *w, int task) {
@@ -1396,7 +1508,9 @@ int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, vo
     cudaStream_t st = (cudaStream_t)stream;
     const int g = (w->n + 127) / 128, od = rs_task_obs_dim(w, task);
     const uint32_t off = (uint32_t)w->env_offset;
-    push_t(w, st);
+    const int rc = push_t(w, st);
+    if (rc) return rc;
+    w->chain_ok = false;
     const uint32_t *t = w->d_ctr;
     if (task == RS_TASK_VSS_V0) k_task_reset<RS_TASK_VSS><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
     else if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) k_task_reset<RS_TASK_SSL_STATIC_DEFENDERS><<<g, 128, 0, st>>>(w->dp, state_ptrs(w), d_mask, d_obs, od, w->seed, t, off);
@@ -1409,23 +1523,33 @@ int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, vo
 }
 
 // One launch of VSSEnv.step over the S.n matches S / A point at.
-static void launch_vss(rs_world *w, const VssStepArgs &A, const StatePtrs &S, cudaStream_t st) {
+static void launch_vss(rs_world *w, VssStepArgs &A, const StatePtrs &S, cudaStream_t st) {
     const int n = S.n;
+    A.flags = nullptr; A.chain = 0;
     if (use_lane_per_body(w, true)) {
-        if (w->lane_block == 256) launch_step_kernel(k_vss_env_step_lanes<256>, (n + 31) / 32, 256, st, w->dp, S, A);
-        else if (w->lane_block == 64) launch_step_kernel(k_vss_env_step_lanes<64>, (n + 7) / 8, 64, st, w->dp, S, A);
-        else if (w->f0) launch_step_kernel(k_vss_env_step_lanes<128, true>, (n + 15) / 16, 128, st, w->dp, S, A);
-        else launch_step_kernel(k_vss_env_step_lanes<128>, (n + 15) / 16, 128, st, w->dp, S, A);
-    } else if (w->f0 && use_packed(w)) switch (w->block) {
-        case 32: launch_step_kernel(k_vss_env_step<3, 3, 32, 2>, (n + 31) / 32, 32, st, w->dp, S, A); break;
-        case 128: launch_step_kernel(k_vss_env_step<3, 3, 128, 2>, (n + 127) / 128, 128, st, w->dp, S, A); break;
-        default: launch_step_kernel(k_vss_env_step<3, 3, 64, 2>, (n + 63) / 64, 64, st, w->dp, S, A); break;
-    } else if (w->f0) {
-        launch_step_kernel(k_vss_env_step<3, 3, 64, 1>, (n + 63) / 64, 64, st, w->dp, S, A);
-    } else {
-        launch_step_kernel(k_vss_env_step<3, 3, 64, 0>, (n + 63) / 64, 64, st, w->dp, S, A);
+        w->chain_ok = false;
+        if (w->lane_block == 256) launch_step_kernel(w, k_vss_env_step_lanes<256>, (n + 31) / 32, 256, st, w->dp, S, A);
+        else if (w->lane_block == 64) launch_step_kernel(w, k_vss_env_step_lanes<64>, (n + 7) / 8, 64, st, w->dp, S, A);
+        else if (w->f0) launch_step_kernel(w, k_vss_env_step_lanes<128, true>, (n + 15) / 16, 128, st, w->dp, S, A);
+        else launch_step_kernel(w, k_vss_env_step_lanes<128>, (n + 15) / 16, 128, st, w->dp, S, A);
+        return;
     }
-    w->launches++;
+    // step-to-step overlap: this launch takes part in the tile-flag protocol when the option is on, and may skip
+    // the grid-wide wait when the launch before it (same world, same stream) took part too
+    if (w->overlap) {
+        A.flags = w->d_flags;
+        if (w->pdl && w->chain_ok && w->chain_stream == st) A.chain = w->overlap;
+    }
+    w->chain_ok = w->overlap != 0; w->chain_stream = st;
+    if (w->f0 && use_packed(w)) switch (w->block) {
+        case 32: launch_step_kernel(w, k_vss_env_step<3, 3, 32, 2>, (n + 31) / 32, 32, st, w->dp, S, A); break;
+        case 128: launch_step_kernel(w, k_vss_env_step<3, 3, 128, 2>, (n + 127) / 128, 128, st, w->dp, S, A); break;
+        default: launch_step_kernel(w, k_vss_env_step<3, 3, 64, 2>, (n + 63) / 64, 64, st, w->dp, S, A); break;
+    } else if (w->f0) {
+        launch_step_kernel(w, k_vss_env_step<3, 3, 64, 1>, (n + 63) / 64, 64, st, w->dp, S, A);
+    } else {
+        launch_step_kernel(w, k_vss_env_step<3, 3, 64, 0>, (n + 63) / 64, 64, st, w->dp, S, A);
+    }
 }
 
 int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals, int auto_reset,
@@ -1443,15 +1567,12 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
     A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.trunc = d_trunc; A.cmds_out = d_cmds_out;
     A.auto_reset = auto_reset; A.max_steps = max_steps;
     cudaStream_t st = (cudaStream_t)stream;
-    push_t(w, st);
+    const int rc = push_t(w, st);
+    if (rc) return rc;
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
-#ifdef RS_X_STAGGER
-    A.stagger_ns = getenv("RS_STAGGER_NS") ? atoi(getenv("RS_STAGGER_NS")) : 0;
-    A.stagger_mode = getenv("RS_STAGGER_MODE") ? atoi(getenv("RS_STAGGER_MODE")) : 0;
-#endif
     launch_vss(w, A, state_ptrs(w), st);
-    w->t++;
-    CUDA_TRY(cudaGetLastError());
+    w->t = (w->t + 1) & 0xFFFFFFFFull;
+    LAUNCH_CHECK("rs_vss_env_step");
     return RS_OK;
 }
 
@@ -1468,35 +1589,37 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
     A.actions = d_actions; A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.trunc = d_trunc;
     A.cmds_out = d_cmds_out; A.auto_reset = auto_reset; A.max_steps = max_steps;
     cudaStream_t st = (cudaStream_t)stream;
-    push_t(w, st);
+    const int rc = push_t(w, st);
+    if (rc) return rc;
+    w->chain_ok = false;
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
     if (task == RS_TASK_SSL_DRIBBLING_V0) {
-        launch_step_kernel(k_ssl_hw_env_step<RS_TASK_SSL_DRIBBLING, 1, 4, 64>, g64, 64, st, w->dp, S, A);
+        launch_step_kernel(w, k_ssl_hw_env_step<RS_TASK_SSL_DRIBBLING, 1, 4, 64>, g64, 64, st, w->dp, S, A);
     } else if (task == RS_TASK_SSL_PASS_ENDURANCE_V0) {
-        launch_step_kernel(k_ssl_hw_env_step<RS_TASK_SSL_PASS_ENDURANCE, 2, 0, 64>, g64, 64, st, w->dp, S, A);
+        launch_step_kernel(w, k_ssl_hw_env_step<RS_TASK_SSL_PASS_ENDURANCE, 2, 0, 64>, g64, 64, st, w->dp, S, A);
     } else if (use_lane_per_body(w, true)) {
         // lane per body: 8 lanes per 1 v 6 match, 4 per 1 v 1 match
         const int bs = w->lane_block;
         if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
-            if (bs == 256) launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 256>, (w->n + 31) / 32, 256, st, w->dp, S, A);
-            else if (bs == 64) launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 64>, (w->n + 7) / 8, 64, st, w->dp, S, A);
-            else launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 128>, (w->n + 15) / 16, 128, st, w->dp, S, A);
+            if (bs == 256) launch_step_kernel(w, k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 256>, (w->n + 31) / 32, 256, st, w->dp, S, A);
+            else if (bs == 64) launch_step_kernel(w, k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 64>, (w->n + 7) / 8, 64, st, w->dp, S, A);
+            else launch_step_kernel(w, k_ssl_env_step_lanes<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 8, 128>, (w->n + 15) / 16, 128, st, w->dp, S, A);
         } else {
-            if (bs == 256) launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 256>, (w->n + 63) / 64, 256, st, w->dp, S, A);
-            else if (bs == 64) launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 64>, (w->n + 15) / 16, 64, st, w->dp, S, A);
-            else launch_step_kernel(k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 128>, (w->n + 31) / 32, 128, st, w->dp, S, A);
+            if (bs == 256) launch_step_kernel(w, k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 256>, (w->n + 63) / 64, 256, st, w->dp, S, A);
+            else if (bs == 64) launch_step_kernel(w, k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 64>, (w->n + 15) / 16, 64, st, w->dp, S, A);
+            else launch_step_kernel(w, k_ssl_env_step_lanes<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 4, 128>, (w->n + 31) / 32, 128, st, w->dp, S, A);
         }
     } else if (task == RS_TASK_SSL_STATIC_DEFENDERS_V0) {
-        if (w->block == 128) launch_step_kernel(k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 128>, g128, 128, st, w->dp, S, A);
-        else launch_step_kernel(k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 64>, g64, 64, st, w->dp, S, A);
+        if (w->block == 128) launch_step_kernel(w, k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 128>, g128, 128, st, w->dp, S, A);
+        else launch_step_kernel(w, k_ssl_env_step<RS_TASK_SSL_STATIC_DEFENDERS, 1, 6, 64>, g64, 64, st, w->dp, S, A);
     } else {
-        if (w->block == 128) launch_step_kernel(k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 128>, g128, 128, st, w->dp, S, A);
-        else launch_step_kernel(k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 64>, g64, 64, st, w->dp, S, A);
+        if (w->block == 128) launch_step_kernel(w, k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 128>, g128, 128, st, w->dp, S, A);
+        else launch_step_kernel(w, k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 64>, g64, 64, st, w->dp, S, A);
     }
-    w->launches++; w->t++;
-    CUDA_TRY(cudaGetLastError());
+    w->t = (w->t + 1) & 0xFFFFFFFFull;
+    LAUNCH_CHECK("rs_ssl_env_step");
     return RS_OK;
 }
 
@@ -1522,12 +1645,17 @@ static int ensure_scratch(rs_world *w, int act_dim, int obs_dim) {
 // into the device address space (UVA): the kernel loads the 8-20 bytes per match straight over
 // PCIe while its state loads are in flight, which saves the separate H2D copy and its latency
 // (248 -> 239 us per 65 536-match VSS-v0 step).  Pageable memory is staged with a copy as before.
+// The pointer lookup is cached per handle: a rollout loop passes the same buffer every step.
 static const float *host_actions_on_device(rs_world *w, const float *h_actions, size_t bytes, cudaStream_t st) {
-    cudaPointerAttributes at;
-    if (!getenv("RS_HOST_COPY_ACTIONS") && cudaPointerGetAttributes(&at, h_actions) == cudaSuccess &&
-        at.type == cudaMemoryTypeHost && at.devicePointer)
-        return static_cast<const float *>(at.devicePointer);
-    cudaGetLastError();
+    if (h_actions != w->h_act_seen) {
+        cudaPointerAttributes at;
+        w->h_act_seen = h_actions; w->h_act_dev = nullptr;
+        if (!w->host_copy_actions && cudaPointerGetAttributes(&at, h_actions) == cudaSuccess &&
+            at.type == cudaMemoryTypeHost && at.devicePointer)
+            w->h_act_dev = static_cast<const float *>(at.devicePointer);
+        cudaGetLastError();
+    }
+    if (w->h_act_dev) return w->h_act_dev;
     if (cudaMemcpyAsync(w->s_actions, h_actions, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
         fail(RS_E_CUDA, std::string("host step: H2D copy of the actions failed: ") + cudaGetErrorString(cudaGetLastError()));
         return nullptr;

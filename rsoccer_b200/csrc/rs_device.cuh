@@ -793,15 +793,18 @@ struct StatePtrs {
     int np;           // padded env count (array pitch)
 };
 
+// State loads bypass L1 (ld.global.cg): every state word is read exactly once per step, and a
+// step kernel that overlaps its predecessor (tile_acquire below) must never hit a line an
+// earlier launch left in this SM's L1.
 template <int RT>
 __device__ __forceinline__ void load_scene(const DevParams &P, const StatePtrs &S, int e, Scene<RT> &s) {
     const int R = RT > 0 ? RT : P.n_robots;
-    const float4 b = S.body[e];
+    const float4 b = __ldcg(S.body + e);
     s.bx = b.x; s.by = b.y; s.bvx = b.z; s.bvy = b.w;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const float4 q = S.body[(size_t)(r + 1) * S.np + e];
-        const float2 a = S.ang[(size_t)r * S.np + e];
+        const float4 q = __ldcg(S.body + (size_t)(r + 1) * S.np + e);
+        const float2 a = __ldcg(S.ang + (size_t)r * S.np + e);
         s.x[r] = q.x; s.y[r] = q.y; s.vx[r] = q.z; s.vy[r] = q.w; s.th[r] = a.x; s.om[r] = a.y;
     }
 }
@@ -866,7 +869,7 @@ __device__ __forceinline__ uint32_t step_counter_read(const uint32_t *ctr, const
     const int lane = threadIdx.x & 31;
     uint32_t t = 0u;
     if ((lane & (GL - 1)) == 0) {
-        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t) : "l"(ctr + e / RS_CTR_GROUP), "l"(l2_keep_policy()) : "memory");
+        asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t) : "l"(ctr + e / RS_CTR_GROUP), "l"(l2_keep_policy()) : "memory");
     }
     return __shfl_sync(live, t, lane & ~(GL - 1));      // a group's first lane is live whenever any of its lanes is
 }
@@ -885,3 +888,46 @@ __device__ __forceinline__ void step_counter_bump(uint32_t *ctr, const int e, co
 // Both are no-ops for launches without the attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------- step-to-step overlap
+// A step kernel normally begins with griddepcontrol.wait: nothing of step k+1 runs before the
+// whole grid of step k has finished AND flushed, so launch ramp, state loads and the store
+// drain of consecutive steps are serialised (~7 of 15.5 us at 65 536 matches).  But match i at
+// step k+1 depends only on match i at step k.  With RS_OPT_STEP_OVERLAP the dependency is
+// tracked per 32-match tile (= one warp of the lane-per-match kernels) through one flag word
+// per tile in device memory (library owned, 0 = ready, 1 = a step is working on the tile):
+//   start of a warp:  lane 0 spins (ld.acquire.gpu) until its tile is ready, marks it busy with
+//                     an atomic exchange (performed at L2 before the warp goes on), then the
+//                     warp calls griddepcontrol.launch_dependents -- so step k+2 cannot launch
+//                     before every tile of step k has been handed to step k+1;
+//   end of a warp:    __syncwarp, lane 0: __threadfence (cumulative: covers the stores of the
+//                     whole warp), then marks the tile ready.
+// No deadlock: a programmatic launch starts only after EVERY CTA of the predecessor has
+// executed launch_dependents, i.e. is resident, so a spinning warp always waits for a running
+// one.  The spin is bounded anyway (RS_SPIN_LIMIT polls, then the tile error word is set and the
+// warp goes on): a protocol error must not hang the GPU.
+#ifndef RS_SPIN_LIMIT
+#define RS_SPIN_LIMIT (1 << 20)
+#endif
+__device__ __forceinline__ void tile_acquire(uint32_t *flag, uint32_t *err) {
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t v;
+        int spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == 0u || ++spins > RS_SPIN_LIMIT) break;
+            __nanosleep(40);
+        }
+        uint32_t old;
+        asm volatile("atom.exch.acquire.gpu.global.b32 %0, [%1], %2;" : "=r"(old) : "l"(flag), "r"(1u) : "memory");
+        if (old != 0u) atomicAdd(err, 1u);     // timed out, or two steps of one world on different streams
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void tile_release(uint32_t *flag) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(0u) : "memory");
+    }
+}

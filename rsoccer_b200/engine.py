@@ -39,6 +39,10 @@ class BatchedWorld:
             raise _lib.RsError("rsoccer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.L = _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.RsError("rsoccer_b200 worlds live on a CUDA device, not on %r" % (self.device,))
+        if self.device.index is None:          # "cuda" = the current device, resolved once
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.kind, self.field_type = int(kind), int(field_type)
         self.n_blue, self.n_yellow = int(n_blue), int(n_yellow)
         self.R = self.n_blue + self.n_yellow
@@ -68,8 +72,12 @@ class BatchedWorld:
         self.body = view(_lib.ARR_BODY, 16 * (R + 1) * Np, torch.float32, (R + 1, Np, 4))
         self.ang = view(_lib.ARR_ANG, 8 * R * Np, torch.float32, (R, Np, 2))
         self.ou = view(_lib.ARR_OU, 8 * max(R - 1, 1) * Np, torch.float32, (max(R - 1, 1), Np, 2))
-        self.prev_pot = view(_lib.ARR_PREV, 4 * Np, torch.float32, (Np,))
-        self.steps = view(_lib.ARR_STEPS, 4 * Np, torch.int32, (Np,))
+        # one float task word per match: the previous ball potential (VSS-v0), checkpoints_count
+        # (SSLDribbling-v0, dribbling.py:56) or stopped_steps (SSLPassEndurance-v0, pass_endurance.py:57)
+        self.task_word = view(_lib.ARR_PREV, 4 * Np, torch.float32, (Np,))
+        self.prev_pot = self.task_word
+        # raw step word: bits 0-23 = episode step count, bit 24 = "previous potential valid" (VSS-v0)
+        self.steps_raw = view(_lib.ARR_STEPS, 4 * Np, torch.int32, (Np,))
         self.info = view(_lib.ARR_INFO, 4 * 9 * Np, torch.float32, (9, Np))
 
     # ------------------------------------------------------------------ plumbing
@@ -105,6 +113,24 @@ class BatchedWorld:
         """Read the device-resident step counter back (needed after CUDA-graph replays)."""
         _lib.check(self.L.rs_sync_t(self.h, self._stream()), "rs_sync_t")
         return self.t
+
+    @property
+    def steps(self):
+        """episode step count per match (a copy: the flag bit of the raw word is masked off)"""
+        return self.steps_raw & 0xFFFFFF
+
+    def set_option(self, option, value):
+        """rs_set_option: e.g. set_option(_lib.OPT_STEP_OVERLAP, 1), see include/rsoccer_b200.h"""
+        _lib.check(self.L.rs_set_option(self.h, int(option), int(value)), "rs_set_option")
+
+    def get_option(self, option):
+        v = C.c_int64()
+        _lib.check(self.L.rs_get_option(self.h, int(option), C.byref(v), self._stream()), "rs_get_option")
+        return int(v.value)
+
+    def state_written(self):
+        """call after writing the state through the zero-copy views while step overlap is on"""
+        self.set_option(_lib.OPT_STEP_OVERLAP, self.get_option(_lib.OPT_STEP_OVERLAP))
 
     @property
     def launches(self):

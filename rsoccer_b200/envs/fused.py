@@ -13,6 +13,10 @@ API (gymnasium VectorEnv flavour, same-step auto-reset):
 per key (zero-copy views of the on-device accumulators).  When an episode ends the returned
 observation is the first one of the next episode; `truncated` follows the registered step
 limits (rsoccer_gym/__init__.py:3-30).
+
+Aliasing: `step` / `reset` return the SAME preallocated tensors on every call (zero-copy: the
+kernel writes them in place).  A rollout buffer must copy what it keeps (`buf[t].copy_(obs)`),
+or construct the env with `copy_outputs=True` to get fresh tensors from every call.
 """
 import torch
 
@@ -36,7 +40,7 @@ class _FusedVecEnv:
     NORM_BOUNDS = 1.2
 
     def __init__(self, num_envs=1, device=None, seed=0, env_offset=0, auto_reset=True, max_episode_steps=None,
-                 field_type=None, render_mode=None):
+                 field_type=None, render_mode=None, copy_outputs=False):
         if render_mode not in (None, "rgb_array"):
             raise NotImplementedError("render_mode %r: only 'rgb_array' (no window) is offered" % (render_mode,))
         self.render_mode = render_mode
@@ -53,16 +57,21 @@ class _FusedVecEnv:
         self.action_space = BoxSpec(-1.0, 1.0, (self.num_envs, self.ACT_DIM))
         self.observation_space = BoxSpec(-self.NORM_BOUNDS, self.NORM_BOUNDS, (self.num_envs, self.obs_dim))
         self._out = self.world.alloc_outputs(self.TASK)
+        self.copy_outputs = bool(copy_outputs)
         self._pinned = None
         self.field = None
 
     # ---- gym surface
     def reset(self, *, seed=None, options=None, mask=None):
-        obs = self.world.task_reset(self.TASK, mask=mask, obs=self._out[0] if mask is None else None)
-        return obs, self.info()
+        # a masked reset rewrites only the rows of the selected matches: the others keep their
+        # current observation (the one the last step wrote into the same tensor)
+        obs = self.world.task_reset(self.TASK, mask=mask, obs=self._out[0])
+        return (obs.clone() if self.copy_outputs else obs), self.info()
 
     def step(self, actions):
         obs, rew, done, trunc = self._step(actions)
+        if self.copy_outputs:
+            obs, rew = obs.clone(), rew.clone()
         return obs, rew, done.bool(), trunc.bool(), self.info()
 
     def step_raw(self, actions):
@@ -147,7 +156,7 @@ class SSLDribblingVecEnv(_SSLFused):
 
     @property
     def checkpoints(self):
-        return self.world.prev_pot[:self.num_envs]
+        return self.world.task_word[:self.num_envs]
 
 
 class SSLPassEnduranceVecEnv(_SSLFused):

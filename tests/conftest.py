@@ -29,13 +29,18 @@ def _engine_module():
     return E
 
 
-@pytest.fixture(params=["per_match", "per_match_packed", "per_body"])
+@pytest.fixture(params=["per_match", "per_match_packed", "per_body", "per_match_overlap"])
 def engine(request, monkeypatch, _engine_module):
     """The CUDA engine, once per kernel family: rs_create reads RS_PER_MATCH (1 = one lane
     per match, rs_device.cuh; 0 = one lane per body, rs_lanes.cuh; unset = by world size) and
     RS_PACKED (1 = the packed fp32x2 instruction forms of the large-world VSS-v0 kernel, 0 = the
     scalar forms; unset = by world size), so every GPU test exercises all of them whatever the
-    size heuristics would pick."""
+    size heuristics would pick.  "per_match_overlap" also turns the step-to-step overlap protocol
+    on (RS_STEP_OVERLAP=2, include/rsoccer_b200.h): every test then runs with the tile flags."""
     monkeypatch.setenv("RS_PER_MATCH", "0" if request.param == "per_body" else "1")
-    monkeypatch.setenv("RS_PACKED", "1" if request.param == "per_match_packed" else "0")
+    monkeypatch.setenv("RS_PACKED", "0" if request.param in ("per_match", "per_body") else "1")
+    if request.param == "per_match_overlap":
+        monkeypatch.setenv("RS_STEP_OVERLAP", "2")
+    else:
+        monkeypatch.delenv("RS_STEP_OVERLAP", raising=False)
     return _engine_module

@@ -301,3 +301,171 @@ def test_render_rgb_array_of_env_i_of_a_batch(engine):
     ssl = envs.make("SSLStaticDefenders-v0", num_envs=2, render_mode="rgb_array")
     ssl.reset()
     assert ssl.render(1, width_px=400).shape[1] == 400
+
+
+def _twin_worlds(E, n, seed, modes):
+    ws = []
+    for m in modes:
+        w = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=seed)
+        w.set_option(_lib_consts().OPT_STEP_OVERLAP, m)
+        w.task_reset(E.TASK_VSS_V0)
+        ws.append(w)
+    return ws
+
+
+def _lib_consts():
+    from rsoccer_b200 import _lib
+    return _lib
+
+
+@pytest.mark.parametrize("n", [65536, 5000, 33])
+def test_step_overlap_modes_are_bit_identical(_engine_module, monkeypatch, n):
+    """RS_OPT_STEP_OVERLAP: consecutive steps synchronise per 32-match tile instead of grid-wide.
+    Same kernels, same arithmetic, only the waiting differs -- so after hundreds of back-to-back
+    steps (direct launches and CUDA-graph replays, nothing enqueued in between, fixed action
+    buffer) every mode must leave the world in the same state bit for bit; a tile that started on
+    stale state would diverge chaotically.  33 and 5 000 matches leave ragged tiles / dead warps."""
+    E, L = _engine_module, _lib_consts()
+    monkeypatch.setenv("RS_PER_MATCH", "1")
+    monkeypatch.delenv("RS_STEP_OVERLAP", raising=False)
+    ws = _twin_worlds(E, n, 11, (0, 1, 2))
+    assert [w.get_option(L.OPT_STEP_OVERLAP) for w in ws] == [0, 1, 2]
+    a = (torch.rand(n, 2, device="cuda") * 2 - 1)
+    outs = [w.alloc_outputs(E.TASK_VSS_V0) for w in ws]
+    s = torch.cuda.Stream()
+    finals = []
+    for w, out in zip(ws, outs):
+        with torch.cuda.stream(s):
+            for _ in range(150):
+                w.vss_env_step(a, out=out, max_steps=40)
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(25):
+                    w.vss_env_step(a, out=out, max_steps=40)
+            for _ in range(8):
+                g.replay()
+            s.synchronize()
+        assert w.get_option(L.OPT_OVERLAP_ERRORS) == 0
+        finals.append((w.state.clone(), [o.clone() for o in out], w.sync_t()))
+    assert finals[0][2] == 150 + 200
+    for f in finals[1:]:
+        assert f[2] == finals[0][2]
+        assert torch.equal(f[0], finals[0][0])
+        assert all(torch.equal(x, y) for x, y in zip(f[1], finals[0][1]))
+
+
+def test_step_overlap_survives_interleaved_calls(_engine_module, monkeypatch):
+    """anything else that touches the state between two steps (reset, set_raw, rs_step, a masked task
+    reset, an option change) puts the next step back on the grid-wide wait: same results as mode 0"""
+    E, L = _engine_module, _lib_consts()
+    monkeypatch.setenv("RS_PER_MATCH", "1")
+    n = 4096
+    w0, w2 = _twin_worlds(E, n, 5, (0, 2))
+    a = (torch.rand(n, 2, device="cuda") * 2 - 1)
+    cmds = torch.rand(n, 6, 2, device="cuda") * 20 - 10
+    mask = (torch.arange(n, device="cuda") % 3 == 0)
+    for w in (w0, w2):
+        for i in range(60):
+            w.vss_env_step(a)
+            if i % 7 == 3:
+                w.step(cmds)
+            if i % 11 == 5:
+                w.task_reset(E.TASK_VSS_V0, mask=mask)
+            if i % 13 == 6:
+                w.set_raw(w.get_raw())
+            if i % 17 == 8:
+                w.state_written()
+        torch.cuda.synchronize()
+    assert w2.get_option(L.OPT_OVERLAP_ERRORS) == 0
+    assert torch.equal(w0.state, w2.state) and w0.sync_t() == w2.sync_t()
+
+
+def test_rs_step_between_graph_replays_does_not_rewind_the_noise(_engine_module, monkeypatch):
+    """rs_step draws no random numbers and must leave the device-authoritative step counter alone:
+    graph replays, then rs_step, then more replays == the same sequence launched eagerly"""
+    E = _engine_module
+    monkeypatch.setenv("RS_PER_MATCH", "1")
+    n = 512
+    a = torch.rand(n, 2, device="cuda") * 2 - 1
+    cmds = torch.rand(n, 6, 2, device="cuda") * 20 - 10
+    w = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=4)
+    w.task_reset(E.TASK_VSS_V0)
+    out = w.alloc_outputs(E.TASK_VSS_V0)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        w.vss_env_step(a, out=out)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            w.vss_env_step(a, out=out)
+        for _ in range(3):
+            g.replay()
+        w.step(cmds)
+        for _ in range(2):
+            g.replay()
+        s.synchronize()
+    assert w.sync_t() == 6
+    ref = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=4)
+    ref.task_reset(E.TASK_VSS_V0)
+    for _ in range(4):
+        ref.vss_env_step(a)
+    ref.step(cmds)
+    for _ in range(2):
+        ref.vss_env_step(a)
+    assert ref.t == 6 and torch.equal(ref.state, w.state)
+    # a pending rs_set_t must not be baked into a graph
+    w.t = 3
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with pytest.raises(Exception):
+            with torch.cuda.graph(g2, stream=s):
+                w.vss_env_step(a, out=out)
+    with pytest.raises(Exception):
+        w.t = 1 << 32
+
+
+def test_options_are_per_handle(_engine_module, monkeypatch):
+    """no process-global switches: two handles created under different RS_PDL settings coexist and agree"""
+    E, L = _engine_module, _lib_consts()
+    n = 2048
+    monkeypatch.setenv("RS_PDL", "0")
+    w0 = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=2)
+    monkeypatch.setenv("RS_PDL", "1")
+    w1 = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=2)
+    monkeypatch.delenv("RS_PDL")
+    assert (w0.get_option(L.OPT_PDL), w1.get_option(L.OPT_PDL)) == (0, 1)
+    a = torch.rand(n, 2, device="cuda") * 2 - 1
+    for w in (w0, w1):
+        w.task_reset(E.TASK_VSS_V0)
+    for _ in range(20):
+        w0.vss_env_step(a); w1.vss_env_step(a)
+    assert torch.equal(w0.state, w1.state)
+    w1.set_option(L.OPT_PDL, 0)
+    assert w1.get_option(L.OPT_PDL) == 0 and w0.get_option(L.OPT_PDL) == 0
+    with pytest.raises(Exception):
+        w0.set_option(99, 1)
+
+
+def test_world_runs_on_its_own_device_whatever_is_current(_engine_module):
+    """every entry point selects the world's device and restores the caller's (two worlds on two GPUs
+    in one process; device="cuda" resolves to the current device)"""
+    E = _engine_module
+    assert E.BatchedWorld(0, 0, 3, 3, 25, 8, device="cuda").device.index == torch.cuda.current_device()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 1024
+    a = torch.rand(n, 2) * 2 - 1
+    w0 = E.BatchedWorld(0, 0, 3, 3, 25, n, device="cuda:0", seed=6)
+    w1 = E.BatchedWorld(0, 0, 3, 3, 25, n, device="cuda:1", seed=6)
+    a0, a1 = a.to("cuda:0"), a.to("cuda:1")
+    with torch.cuda.device(0):                  # cuda:0 stays current while cuda:1's world is stepped
+        for w in (w0, w1):
+            w.task_reset(E.TASK_VSS_V0)
+        for _ in range(10):
+            w0.vss_env_step(a0); w1.vss_env_step(a1)
+        h0, h1 = w0.alloc_host_outputs(E.TASK_VSS_V0), w1.alloc_host_outputs(E.TASK_VSS_V0)
+        ha = a.pin_memory()
+        w0.vss_env_step_host(ha, *h0); w1.vss_env_step_host(ha, *h1)
+        assert torch.cuda.current_device() == 0
+    assert torch.equal(w0.state.cpu(), w1.state.cpu()) and torch.equal(h0[0], h1[0])

@@ -155,3 +155,17 @@ def test_oracle_physics_is_mirror_symmetric(oracle):
     assert run(O.KIND_SSL, 2, 1, 6, 256, 10, False)[0] == 0
     bad, worst = run(O.KIND_SSL, 2, 1, 6, 256, 2, True)
     assert worst < 1e-12                     # symmetric to rounding, not to the bit
+
+
+def test_dropin_harness_agrees_with_itself():
+    """tests/dropin_check.py (the -m gpu drop-in test) with the oracle on BOTH sides: the re-sync of
+    two unmodified reference envs (raw state, OU state, counters, np.random stream) is exact, so any
+    difference the GPU run reports is the engine's, not the harness's"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dropin_check import reference_path
+    if reference_path() is None:
+        pytest.skip("reference package not installed (baseline/_ref)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_check.py"), "40"], capture_output=True,
+                       text=True, timeout=600, env=dict(os.environ, RS_DROPIN_SELFCHECK="1"))
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-2000:] + r.stderr[-2000:]
+    assert "max |obs_cuda - obs_oracle| = 0.00e+00" in r.stdout
