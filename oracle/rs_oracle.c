@@ -113,6 +113,14 @@ static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x >
  * dynamics keep centres >= one radius apart) counts as ill conditioned at margin 2e-5 */
 #define NORMAL_COND 4e-3
 static void note(double *margin, double m) { m = fabs(m); if (m < *margin) *margin = m; }
+/* A contact / wall decision is discontinuous only in the velocity impulse it triggers: the
+ * position correction it adds is the penetration, which vanishes AT the boundary.  So a decision
+ * decided by a hair matters only when the impulse on the other side of it is not negligible:
+ * `jump` = the normal velocity change the contact would apply [m/s].  A robot resting on a wall
+ * (velocity already zeroed, centre exactly on the limit) or two bodies sliding apart are decided
+ * by 0 m and yet give the same result either way -- they are not ill conditioned. */
+#define JUMP_TOL 2e-5
+static void note_jump(double *margin, double m, double jump) { if (fabs(jump) > JUMP_TOL) note(margin, m); }
 
 /* kicker "touching" box, in the robot frame (grSim isTouchingBall analogue).
  * K7: true with the ball 0.1 m ahead (dribbling.py:193-195, contested_possession.py:224-225). */
@@ -144,7 +152,10 @@ static int ball_robot_contact(const rs_params *p, const o_robot *r, const o_ball
     double d2 = dx * dx + dy * dy;
     if (p->kind == RS_KIND_VSS) {
         double rs = R + rb;
-        note(margin, sqrt(d2) - rs);
+        {   /* discs: the lever arm is parallel to the normal, omega does not enter the normal velocity */
+            double d = sqrt(d2), vn = d > 0 ? ((b->vx - r->vx) * dx + (b->vy - r->vy) * dy) / d : -1.0;
+            note_jump(margin, d - rs, vn < 0 ? (1.0 + p->e_ball_rbt) * vn : 0.0);
+        }
         if (d2 >= rs * rs) return 0;
         double d = sqrt(d2);
         note(margin, d * NORMAL_COND);
@@ -153,7 +164,11 @@ static int ball_robot_contact(const rs_params *p, const o_robot *r, const o_ball
         *rcx = *nx * R; *rcy = *ny * R;
         return 1;
     }
-    if (d2 >= (R + rb) * (R + rb)) { note(margin, sqrt(d2) - (R + rb)); return 0; }
+    if (d2 >= (R + rb) * (R + rb)) {
+        double d = sqrt(d2), vn = ((b->vx - r->vx) * dx + (b->vy - r->vy) * dy) / d;
+        note_jump(margin, d - (R + rb), vn < 0 ? (1.0 + p->e_ball_rbt) * vn : 0.0);
+        return 0;
+    }
     double c = cos(r->th), s = sin(r->th);
     double lx = c * dx + s * dy, ly = -s * dx + c * dy;
     double dk = p->rbt_distance_center_kicker, ch = p->mouth_half_chord;
@@ -165,7 +180,12 @@ static int ball_robot_contact(const rs_params *p, const o_robot *r, const o_ball
     else { qx = dk; qy = clampd(ly, -ch, ch); }
     double ex = lx - qx, ey = ly - qy;
     double e2 = ex * ex + ey * ey;
-    note(margin, sqrt(e2) - rb);
+    if (e2 > 1e-12) {   /* the impulse this contact applies (or would apply): surface velocity at the closest point */
+        double e = sqrt(e2), wnx = (c * ex - s * ey) / e, wny = (s * ex + c * ey) / e;
+        double wrx = c * qx - s * qy, wry = s * qx + c * qy;
+        double vn = (b->vx - (r->vx - r->om * wry)) * wnx + (b->vy - (r->vy + r->om * wrx)) * wny;
+        note_jump(margin, e - rb, vn < 0 ? (1.0 + p->e_ball_rbt) * vn : 0.0);
+    } else note(margin, sqrt(e2) - rb);
     if (e2 >= rb * rb) return 0;
     double lnx, lny;
     if (e2 > 1e-12) {
@@ -198,7 +218,10 @@ static void walls(const rs_params *p, double r, double e, double *x, double *y,
             double qx = clampd(ax, bx[0], bx[2]), qy = clampd(ay, bx[1], bx[3]);
             double dx = ax - qx, dy = ay - qy;
             double d2 = dx * dx + dy * dy;
-            note(margin, sqrt(d2) - r);
+            if (d2 > 1e-12) {
+                double d = sqrt(d2), vn = (avx * dx + avy * dy) / d;
+                note_jump(margin, d - r, vn < 0 ? (1.0 + e) * vn : 0.0);
+            } else note(margin, sqrt(d2) - r);
             if (d2 >= r * r) continue;
             double nx, ny, pen;
             if (d2 > 1e-12) {
@@ -219,9 +242,9 @@ static void walls(const rs_params *p, double r, double e, double *x, double *y,
             if (vn < 0) { avx -= (1.0 + e) * vn * nx; avy -= (1.0 + e) * vn * ny; }
         }
     }
-    note(margin, ax - (p->x_out - r));
+    note_jump(margin, ax - (p->x_out - r), avx > 0 ? (1.0 + e) * avx : 0.0);
     if (ax > p->x_out - r) { ax = p->x_out - r; if (avx > 0) avx = -e * avx; }
-    note(margin, ay - (p->y_out - r));
+    note_jump(margin, ay - (p->y_out - r), avy > 0 ? (1.0 + e) * avy : 0.0);
     if (ay > p->y_out - r) { ay = p->y_out - r; if (avy > 0) avy = -e * avy; }
     *x = sx * ax; *y = sy * ay; *vx = sx * avx; *vy = sy * avy;
 }
@@ -357,7 +380,10 @@ static void step_env(const rs_params *p, o_ball *b, o_robot *rb, const double *c
         for (int i = 0; i < R; ++i) for (int j = i + 1; j < R; ++j) {
             double dx = rb[j].x - rb[i].x, dy = rb[j].y - rb[i].y;
             double d2 = dx * dx + dy * dy, rs = 2.0 * p->rbt_radius;
-            note(margin, sqrt(d2) - rs);
+            {
+                double d = sqrt(d2), vn = d > 0 ? ((rb[j].vx - rb[i].vx) * dx + (rb[j].vy - rb[i].vy) * dy) / d : -1.0;
+                note_jump(margin, d - rs, vn < 0 ? (1.0 + p->e_rbt_rbt) * vn : 0.0);
+            }
             if (d2 >= rs * rs) continue;
             double d = sqrt(d2), nx, ny;
             note(margin, d * NORMAL_COND);

@@ -86,6 +86,9 @@ def run_vss(seed, steps, scripted):
             side = 1.0 if (t // 40) % 2 == 0 else -1.0
             raw[0], raw[1], raw[2], raw[3] = side * 0.66, rng.uniform(-0.1, 0.1), side * 1.5, 0.0
             set_raw(env, raw)
+        if scripted and t % 40 == 35:      # one step short of the registered limit (rsoccer_gym/__init__.py:4): TimeLimit fires
+            u.steps = 1199
+            env._elapsed_steps = 1199
         rec["raw_before"].append(raw_of(env))
         rec["ou_before"].append(np.concatenate([np.asarray(u.ou_actions[i].x_prev, dtype=np.float64) for i in range(1, 6)]))
         rec["prev_pot"].append(0.0 if u.previous_ball_potential is None else float(u.previous_ball_potential))
@@ -160,6 +163,87 @@ def run_ssl(env_id, seed, steps, scripted):
     out = {k: np.array(v) for k, v in rec.items()}
     out["field"] = np.array([getattr(u.field, k) for k in u.field.__dataclass_fields__])
     out["info_keys"] = np.array(list(info.keys()))
+    return out
+
+
+BRANCH_KEYS = ("goal", "rbt_in_gk_area", "done_ball_out", "done_ball_out_right", "done_rbt_out", "collision")
+
+
+def run_ssl_branches(env_id, seed, reps=4):
+    """Every branch of the done chain (static_defenders.py:179-198, contested_possession.py:165-191) and a
+    TimeLimit truncation, `reps` times each: one scripted frame per recorded step.  `branch` = index in
+    BRANCH_KEYS of the reward_shaping_total counter the reference incremented (-1: none)."""
+    random.seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env = gym.make(env_id)
+    u = env.unwrapped
+    nb, ny = u.n_robots_blue, u.n_robots_yellow
+    R = nb + ny
+    limit = env._max_episode_steps
+    scen = ["goal", "ball_out_right", "ball_out_left", "ball_out_side", "rbt_out_left", "rbt_out_side",
+            "rbt_in_gk", "trunc", "shaping"] + (["collision"] if "Contested" in env_id else [])
+    rec = {k: [] for k in ("raw_before", "steps_before", "action", "cmds", "obs", "reward", "done", "trunc",
+                           "state_after", "raw_after", "branch")}
+    names = []
+    for rep in range(reps):
+        for name in scen:
+            env.reset()
+            raw = raw_of(env)
+            j = lambda s=0.02: rng.uniform(-s, s)                       # noqa: E731
+            for k in range(ny):                                        # defenders parked along the lower touch line
+                raw[4 + 6 * (nb + k):4 + 6 * (nb + k) + 6] = (0.4 + 0.4 * k, -1.7, 0.0, 0.0, 0.0, 0.0)
+            rb = [1.0 + j(0.2), 0.5 + j(0.2), rng.uniform(-3, 3), 0.0, 0.0, 0.0]
+            ball = [1.5 + j(0.2), 0.2 + j(0.2), 0.0, 0.0]
+            side = 1.0 if rep % 2 == 0 else -1.0
+            if name == "goal":
+                ball = [2.97 + j(0.01), 0.25 * side + j(), 3.0, j(0.2)]
+            elif name == "ball_out_right":
+                ball = [2.97 + j(0.01), 1.0 * side + j(0.3), 3.0, j(0.2)]
+            elif name == "ball_out_left":
+                ball = [0.03 + j(0.01), 0.3 * side + j(0.2), -3.0, j(0.2)]
+            elif name == "ball_out_side":
+                ball = [1.0 + j(0.3), 1.97 * side, j(0.2), 3.0 * side]
+            elif name == "rbt_out_left":
+                rb[0], rb[1] = -0.25 + j(0.02), 0.3 * side
+            elif name == "rbt_out_side":
+                rb[0], rb[1] = 1.0 + j(0.3), 2.05 * side
+            elif name == "rbt_in_gk":
+                rb[0], rb[1] = 2.5 + j(0.1), 0.4 * side + j(0.2)
+            elif name == "collision":
+                yx, yy = 1.5 + j(0.2), 0.6 * side
+                raw[4 + 6 * nb:4 + 6 * nb + 6] = (yx, yy, np.pi, 0.0, 0.0, 0.0)
+                rb = [yx - 0.185, yy + j(0.01), 0.0, 1.5, 0.0, 0.0]
+                ball = [0.8, -0.8 * side, 0.0, 0.0]
+            raw[0:4] = ball
+            raw[4:10] = rb
+            set_raw(env, raw)
+            if name == "trunc":
+                u.steps = limit - 1
+                env._elapsed_steps = limit - 1
+            rec["raw_before"].append(raw_of(env))
+            rec["steps_before"].append(u.steps)
+            a = rng.uniform(-1, 1, 5).astype(np.float32)
+            before = dict(u.reward_shaping_total or {})
+            obs, rew, term, trunc, info = env.step(a)
+            inc = [i for i, k in enumerate(BRANCH_KEYS) if info.get(k, 0) - before.get(k, 0) > 0]
+            assert len(inc) <= 2, (name, inc)
+            rec["branch"].append(inc[0] if inc else -1)
+            rec["action"].append(a.astype(np.float64))
+            cm = np.zeros((R, 8))
+            for c in u.sent_commands:
+                row = (nb + c.id) if c.yellow else c.id
+                cm[row] = (c.wheel_speed, c.v_x, c.v_y, c.v_theta, 0.0, c.kick_v_x, c.kick_v_z, c.dribbler)
+            rec["cmds"].append(cm.reshape(-1))
+            rec["obs"].append(obs.astype(np.float64))
+            rec["reward"].append(float(rew)); rec["done"].append(int(term)); rec["trunc"].append(int(trunc))
+            rec["state_after"].append(np.array(u.rsim.simulator.get_state()))
+            rec["raw_after"].append(raw_of(env))
+            names.append(name)
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["scenario"] = np.array(names)
+    out["branch_keys"] = np.array(BRANCH_KEYS)
+    out["field"] = np.array([getattr(u.field, k) for k in u.field.__dataclass_fields__])
     return out
 
 
@@ -246,6 +330,10 @@ def main():
                         **run_ssl("SSLContestedPossession-v0", 31, 200, False))
     np.savez_compressed(os.path.join(HERE, "ssl_contested_possession_fetch.npz"),
                         **run_ssl("SSLContestedPossession-v0", 32, 240, True))
+    np.savez_compressed(os.path.join(HERE, "ssl_static_defenders_branches.npz"),
+                        **run_ssl_branches("SSLStaticDefenders-v0", 23))
+    np.savez_compressed(os.path.join(HERE, "ssl_contested_possession_branches.npz"),
+                        **run_ssl_branches("SSLContestedPossession-v0", 33))
     np.savez_compressed(os.path.join(HERE, "ssl_dribbling_random.npz"), **run_ssl_hw("SSLDribbling-v0", 41, 200, False))
     np.savez_compressed(os.path.join(HERE, "ssl_dribbling_course.npz"), **run_ssl_hw("SSLDribbling-v0", 42, 300, True))
     np.savez_compressed(os.path.join(HERE, "ssl_pass_endurance_random.npz"),

@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from parity import TOL, check_close, random_raw, raw_diff
+from parity import (RESYNC_CASES, RESYNC_EPS, RESYNC_MAX_FLAGGED, TOL, check_close, random_cmds, random_raw, raw_diff,
+                    resynced_scene)
 
 pytestmark = pytest.mark.gpu
 
@@ -14,56 +15,30 @@ def _worlds(E, O, kind, ft, nb, ny, n, seed=7, env_offset=0):
     return g, o
 
 
-def _random_cmds(rng, kind, n, R):
-    if kind == 0:
-        c = rng.uniform(-60, 60, (n, R, 2))
-        c[rng.random((n, R)) < 0.2] = 0.0
-        return c.astype(np.float32)
-    c = np.zeros((n, R, 8), dtype=np.float32)
-    c[:, :, 1:3] = rng.uniform(-2.5, 2.5, (n, R, 2))
-    c[:, :, 3] = rng.uniform(-10, 10, (n, R))
-    ws = rng.random((n, R)) < 0.2
-    c[ws, 0] = 1.0
-    c[ws, 1:5] = rng.uniform(-150, 150, (int(ws.sum()), 4))
-    c[:, :, 5] = np.where(rng.random((n, R)) < 0.3, 5.0, 0.0)
-    c[:, :, 7] = (rng.random((n, R)) < 0.4).astype(np.float32)
-    c[rng.random((n, R)) < 0.2] = 0.0
-    return c
-
-
-@pytest.mark.parametrize("kind,ft,nb,ny", [(0, 0, 3, 3), (0, 1, 5, 5), (0, 0, 1, 1), (0, 0, 2, 3),
-                                           (1, 2, 1, 6), (1, 2, 1, 1), (1, 0, 3, 3), (1, 2, 1, 0),
-                                           (1, 2, 1, 4), (1, 2, 2, 0), (1, 1, 11, 11)])
+@pytest.mark.parametrize("kind,ft,nb,ny", RESYNC_CASES)
 def test_step_parity_resynced(engine, oracle, kind, ft, nb, ny):
-    """rs_step vs oracle, one control step from identical random (contact-rich) states."""
+    """rs_step vs oracle, one control step from identical random (contact-rich) states.  Every env the
+    oracle does not flag (a decision taken by < 2e-5 m that triggers an impulse) must agree to 1e-4; the
+    flagged fraction is bounded by its measured value + 2 points (tests/parity.py RESYNC_MAX_FLAGGED)."""
     E, O = engine, oracle
     n, R = (4096 if nb + ny <= 10 else 1000), nb + ny      # 11 v 11: the largest world the reference can build
     g, o = _worlds(E, O, kind, ft, nb, ny, n)
     fp = o.field_params()
     rng = np.random.default_rng(1234 + 10 * kind + R)
-    worst = 0.0
+    worst, worst_fl = 0.0, 0.0
     for it in range(6):
-        raw = random_raw(rng, n, R, fp["length"] / 2 + 0.05, fp["width"] / 2,
-                         v_ball=2.0 if kind else 1.0, v_rbt=1.0, w_rbt=6.0)
-        if kind == 1 and it % 2 == 1:   # put the ball in front of robot 0's mouth in half the envs
-            k = rng.random(n) < 0.5
-            th = raw[:, 4 + 2]
-            d = rng.uniform(0.085, 0.115, n)
-            lat = rng.uniform(-0.05, 0.05, n)
-            raw[k, 0] = (raw[:, 4] + np.cos(th) * d - np.sin(th) * lat)[k]
-            raw[k, 1] = (raw[:, 5] + np.sin(th) * d + np.cos(th) * lat)[k]
-            raw = raw.astype(np.float32).astype(np.float64)
-        cmds = _random_cmds(rng, kind, n, R)
+        raw, cmds = resynced_scene(rng, kind, n, R, fp, it)
         g.set_raw(raw); o.set_raw(raw)
         g.step(cmds); o.step(cmds.astype(np.float64))
         vs = max(1.0, fp["length"] / 2) if kind == 1 else 1.0
         err = raw_diff(g.get_raw().cpu().numpy(), o.get_raw(), R, vel_scale=vs)
-        w, fl = check_close(err, o.margin(), "step kind=%d R=%d it=%d" % (kind, R, it), max_flagged=0.25, eps=2e-5)
-        worst = max(worst, w)
+        w, fl = check_close(err, o.margin(), "step kind=%d R=%d it=%d" % (kind, R, it),
+                            max_flagged=RESYNC_MAX_FLAGGED[(kind, ft, nb, ny)], eps=RESYNC_EPS)
+        worst, worst_fl = max(worst, w), max(worst_fl, fl)
         # the wire format agrees too (degrees, infrared, wheel speeds)
         sg, so = g.get_state().cpu().numpy().astype(np.float64), o.get_state()
         K = 6 if kind == 0 else 11
-        ok = o.margin() >= 2e-5
+        ok = o.margin() >= RESYNC_EPS
         ds = np.abs(sg - so)
         for r in range(R):
             c = 5 + K * r + 2
@@ -75,11 +50,12 @@ def test_step_parity_resynced(engine, oracle, kind, ft, nb, ny):
             if kind == 1:
                 tol[5 + K * r + 7:5 + K * r + 11] = 5e-3 * vs   # wheel rad/s = v / 0.02475
         assert (ds[ok] <= tol).all(), "get_state mismatch %s" % np.argwhere(ds[ok] > tol)[:5]
-    print("worst abs err", worst)
+    print("worst abs err %.3e, flagged fraction %.4f" % (worst, worst_fl))
 
 
 def test_step_parity_free_running(engine, oracle):
-    """40 control steps without re-sync, contact-free envs stay within 1e-3."""
+    """40 control steps (one simulated second) without re-sync: envs in which no decision came within 1 mm
+    (91 % of them: robots curving up the field at 0.1-0.3 m/s, a rolling ball) stay within 1e-3."""
     E, O = engine, oracle
     n, R = 2048, 6
     g, o = _worlds(E, O, 0, 0, 3, 3, n)
@@ -91,22 +67,23 @@ def test_step_parity_free_running(engine, oracle):
     rob[:, :, 2] = rng.uniform(60, 120, (n, 6))
     ball = ball.astype(np.float32); rob = rob.astype(np.float32)
     g.reset(ball, rob[:, :3], rob[:, 3:]); o.reset(ball, rob[:, :3], rob[:, 3:])
-    cmds = rng.uniform(5, 25, (n, 6, 2)).astype(np.float32)
+    cmds = rng.uniform(4, 12, (n, 6, 2)).astype(np.float32)
     cmds[:, :, 1] = cmds[:, :, 0] + rng.uniform(-1, 1, (n, 6))
     mmin = np.full(n, 1e9)
-    for _ in range(10):
+    for _ in range(40):
         g.step(cmds); o.step(cmds.astype(np.float64))
         mmin = np.minimum(mmin, o.margin())
     err = raw_diff(g.get_raw().cpu().numpy(), o.get_raw(), R)
     ok = mmin > 1e-3
-    assert ok.mean() > 0.5
+    assert ok.mean() > 0.85
+    print("free running, 40 steps: max abs err %.3e over %.1f %% of the envs" % (err[ok].max(), 100 * ok.mean()))
     assert err[ok].max() < 1e-3, err[ok].max()
 
 
 def _sync_task(g, o, R):
     raw = g.get_raw().cpu().numpy().astype(np.float64)
     o.set_raw(raw)
-    st = g.steps[:g.n].cpu().numpy()
+    st = g.steps_raw[:g.n].cpu().numpy()
     ou = g.ou[:, :g.n, :].permute(1, 0, 2).reshape(g.n, -1).cpu().numpy().astype(np.float64)
     o.set_task_state(ou=ou[:, :2 * (R - 1)], prev_pot=g.prev_pot[:g.n].cpu().numpy().astype(np.float64),
                      has_prev=((st >> 24) & 1).astype(np.int32), steps=(st & 0xFFFFFF).astype(np.int32),
@@ -154,7 +131,7 @@ def test_vss_env_step_parity(engine, oracle):
         worst["rew"] = max(worst["rew"], check_close(e_rew, m, "reward it=%d" % it, tol=2e-4)[0])
         worst["raw"] = max(worst["raw"], check_close(e_raw, m, "state it=%d" % it)[0])
         ts = o.get_task_state()
-        st = g.steps[:n].cpu().numpy()
+        st = g.steps_raw[:n].cpu().numpy()
         assert ((st & 0xFFFFFF)[ok] == ts["steps"][ok]).all()
         gi = g.info[:, :n].t().cpu().numpy()
         assert np.abs(gi - ts["info"])[ok].max() < 2e-3
@@ -258,8 +235,8 @@ def test_ssl_hw_env_step_parity(engine, oracle, task, nb, ny, max_steps):
             pp = g.prev_pot[:n].cpu().numpy()
             pp[k] = cc[k]
             g.prev_pot[:n] = torch.tensor(pp, device="cuda")
-            st = g.steps[:n].cpu().numpy()
-            g.steps[:n] = torch.tensor(np.maximum(st, 1), device="cuda")
+            st = g.steps_raw[:n].cpu().numpy()
+            g.steps_raw[:n] = torch.tensor(np.maximum(st, 1), device="cuda")
         else:
             rx, ry, rth = raw[:, 10], raw[:, 11], raw[:, 12]
             dd = rng.uniform(0.13, 0.3, n)
@@ -367,7 +344,7 @@ def test_full_size_properties(engine, oracle, n):
         if it % 6 == 5:
             # sampled oracle replay of this step: state, task words and noise of the picked matches
             raw = big.get_raw()[pick].cpu().numpy().astype(np.float64)
-            st = big.steps[:n][pick].cpu().numpy()
+            st = big.steps_raw[:n][pick].cpu().numpy()
             ou = big.ou[:, :n, :][:, pick].permute(1, 0, 2).reshape(512, -1).cpu().numpy().astype(np.float64)
             o.set_raw(raw)
             o.set_task_state(ou=ou, prev_pot=big.prev_pot[:n][pick].cpu().numpy().astype(np.float64),
@@ -420,7 +397,7 @@ def test_vss_step_keeps_a_world_and_its_mirror_image_mirror_images(engine, n):
     b.set_raw(raw * sign)
     tsign = torch.tensor(sign, device="cuda")
     for _ in range(40):
-        c = torch.tensor(_random_cmds(rng, 0, n, R), device="cuda")
+        c = torch.tensor(random_cmds(rng, 0, n, R), device="cuda")
         a.step(c)
         b.step(c.flip(-1).contiguous())
     ra, rb = a.get_raw(), b.get_raw() * tsign
