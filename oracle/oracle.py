@@ -60,6 +60,8 @@ def lib():
         L.orc_destroy.argtypes = [vp]
         L.orc_set_threads.argtypes = [vp, i32]
         L.orc_field_params.argtypes = [vp, vp]
+        L.orc_params_dump.argtypes = [vp, vp]
+        L.orc_params_dump.restype = i32
         L.orc_get_t.restype = u64
         L.orc_get_t.argtypes = [vp]
         L.orc_set_t.argtypes = [vp, u64]
@@ -133,6 +135,22 @@ class OracleWorld:
         out = np.zeros(17)
         self.L.orc_field_params(self.h, _p(out))
         return dict(zip(FIELD_KEYS, out.tolist()))
+
+    def params(self):
+        """the derived parameter block of include/rs_spec.h (walls, masses, drive limits, omni matrices, kicker box)"""
+        out = np.zeros(64)
+        n = self.L.orc_params_dump(self.h, _p(out))
+        assert n == 56, n
+        d = dict(dt=out[0], h=out[1], x_out=out[2], y_out=out[3], x_near=out[4], n_box=int(out[5]),
+                 box=out[6:14].reshape(2, 4).copy())
+        names = ("ball_mass", "rbt_mass", "e_ball_wall", "e_rbt_wall", "e_ball_rbt", "e_rbt_rbt", "mu_ball_rbt",
+                 "ball_decel", "wheel_max_rad_s", "half_track", "acc_fwd", "acc_lat", "acc_ang")
+        d.update(zip(names, out[14:27].tolist()))
+        d["omni_J"] = out[27:39].reshape(4, 3).copy()
+        d["omni_Jpinv"] = out[39:51].reshape(3, 4).copy()
+        d.update(zip(("kick_centre", "kick_reach", "kick_half_width", "mouth_half_chord", "kick_speed_max"),
+                     out[51:56].tolist()))
+        return d
 
     @property
     def t(self):

@@ -467,6 +467,26 @@ void orc_destroy(orc_world *w) {
 void orc_set_threads(orc_world *w, int n) { w->n_threads = n > 0 ? n : 1; }
 void orc_field_params(const orc_world *w, double out[RS_FIELD_KEYS]) { rs_params_field(&w->p, out); }
 const rs_params *orc_params(const orc_world *w) { return &w->p; }
+/* the DERIVED block of include/rs_spec.h (rs_params_fill) in a fixed order, for tests/test_spec_independent.py,
+ * which re-derives it with numpy and hand-computed literals (the header is shared by the library and this oracle,
+ * so a CUDA <-> oracle comparison cannot see a mistake in it).  Returns the number of doubles written (64). */
+int orc_params_dump(const orc_world *w, double *out) {
+    const rs_params *p = &w->p;
+    int k = 0;
+    out[k++] = p->dt; out[k++] = p->h; out[k++] = p->x_out; out[k++] = p->y_out; out[k++] = p->x_near;
+    out[k++] = (double)p->n_box;
+    for (int b = 0; b < RS_MAX_BOXES; ++b) for (int i = 0; i < 4; ++i) out[k++] = p->box[b][i];
+    out[k++] = p->ball_mass; out[k++] = p->rbt_mass;
+    out[k++] = p->e_ball_wall; out[k++] = p->e_rbt_wall; out[k++] = p->e_ball_rbt; out[k++] = p->e_rbt_rbt;
+    out[k++] = p->mu_ball_rbt; out[k++] = p->ball_decel;
+    out[k++] = p->wheel_max_rad_s; out[k++] = p->half_track;
+    out[k++] = p->acc_fwd; out[k++] = p->acc_lat; out[k++] = p->acc_ang;
+    for (int i = 0; i < 4; ++i) for (int a = 0; a < 3; ++a) out[k++] = p->omni_J[i][a];
+    for (int a = 0; a < 3; ++a) for (int i = 0; i < 4; ++i) out[k++] = p->omni_Jpinv[a][i];
+    out[k++] = p->kick_centre; out[k++] = p->kick_reach; out[k++] = p->kick_half_width;
+    out[k++] = p->mouth_half_chord; out[k++] = p->kick_speed_max;
+    return k;
+}
 uint64_t orc_get_t(const orc_world *w) { return w->t; }
 void orc_set_t(orc_world *w, uint64_t t) { w->t = t; }
 

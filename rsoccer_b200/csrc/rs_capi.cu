@@ -26,6 +26,9 @@ __global__ void k_set_ctr(uint32_t *ctr, int n_ctr, uint32_t t) {
 #define RS_VSS_THREADS 448
 #endif
 #define RS_VSS_MINB(BS) ((RS_VSS_THREADS / (BS)) > 0 ? (RS_VSS_THREADS / (BS)) : 1)
+#ifndef RS_VSS_DENSE_THREADS
+#define RS_VSS_DENSE_THREADS 704
+#endif
 
 struct VssStepArgs {
     const float2 *actions;   // [N]
@@ -49,9 +52,16 @@ struct VssStepArgs {
 // VSSEnv.step for BS matches per CTA, one lane per match.  ONE launch = commands (agent +
 // OU noise), 5 physics sub-steps, reward/done/truncation, info accumulators, masked
 // auto-reset and the observation tile (leaves through a TMA bulk store).
+//
+// DENSE: the same source compiled for 11 resident CTAs per SM (80 registers instead of 114, no spills, same
+// instruction count).  A launch that overlaps its predecessor (A.chain != 0) wants as many CTAs of the NEXT
+// step resident as registers allow (65 536 matches at 8 worlds: 12.2 -> 10.5 us per step); a launch that
+// starts on an empty GPU wants its 1 024 CTAs spread over all 148 SMs, 7 per SM -- with DENSE the block
+// scheduler packs them 11 per SM onto 93 SMs (15.8 -> 19.5 us), so the host picks per launch.
 template <int NB, int NY, int BS, int F0 /* 0: run-time physics constants.  1: VssF0's, immediates instead of
-          constant-bank loads.  2: VssF0P, the same with the packed fp32x2 instruction forms (rs_device.cuh) */>
-__global__ void __launch_bounds__(BS, RS_VSS_MINB(BS))
+          constant-bank loads.  2: VssF0P, the same with the packed fp32x2 instruction forms (rs_device.cuh) */,
+          bool DENSE = false>
+__global__ void __launch_bounds__(BS, DENSE ? RS_VSS_DENSE_THREADS / BS : RS_VSS_MINB(BS))
 k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const VssStepArgs A) {
     constexpr int R = NB + NY, NZ = 2 * (R - 1), NOBS = 4 + 7 * NB + 5 * NY;
     constexpr bool PK = F0 == 2 && VssF0P::packed;
@@ -69,7 +79,13 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
     uint32_t *const tile_flag = A.flags ? A.flags + (w0 >> 5) : nullptr;
     if (A.chain == 0) pdl_wait();
-    if (tile_flag) tile_acquire(tile_flag, A.flags + ((S.np + 31) >> 5));
+    if (tile_flag) {
+        tile_acquire(tile_flag, A.flags + ((S.np + 31) >> 5));
+        // the CTA's trigger must not fire before ALL its warps hold their tiles (a CTA counts as triggered
+        // once any of its threads has executed launch_dependents): otherwise step k+2 could start and
+        // wait for a tile that step k+1 has not taken yet
+        if (BS > 32) __syncthreads();
+    }
     pdl_release();
     if (e < S.n) {
         // ---- every global load of the step is issued first: the step counter ahead of the state,
@@ -1544,7 +1560,10 @@ static void launch_vss(rs_world *w, VssStepArgs &A, const StatePtrs &S, cudaStre
     if (w->f0 && use_packed(w)) switch (w->block) {
         case 32: launch_step_kernel(w, k_vss_env_step<3, 3, 32, 2>, (n + 31) / 32, 32, st, w->dp, S, A); break;
         case 128: launch_step_kernel(w, k_vss_env_step<3, 3, 128, 2>, (n + 127) / 128, 128, st, w->dp, S, A); break;
-        default: launch_step_kernel(w, k_vss_env_step<3, 3, 64, 2>, (n + 63) / 64, 64, st, w->dp, S, A); break;
+        default:
+            if (A.chain) launch_step_kernel(w, k_vss_env_step<3, 3, 64, 2, true>, (n + 63) / 64, 64, st, w->dp, S, A);
+            else launch_step_kernel(w, k_vss_env_step<3, 3, 64, 2>, (n + 63) / 64, 64, st, w->dp, S, A);
+            break;
     } else if (w->f0) {
         launch_step_kernel(w, k_vss_env_step<3, 3, 64, 1>, (n + 63) / 64, 64, st, w->dp, S, A);
     } else {
