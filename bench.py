@@ -18,7 +18,7 @@ untimed steps that bring every world to its steady-state contact density, robots
 walls: freshly reset scenes step ~25 % faster) are all reported; config.launch says what ran.
 
 L2 hygiene: one world's per-step traffic (38.8 MB at 65 536 matches) fits the 126 MB L2, so
-the steps rotate over M independent worlds whose combined traffic exceeds 1.6 x L2, and the
+the steps rotate over M independent worlds whose combined traffic exceeds 2.4 x L2, and the
 graph length is a multiple of M: every step reads its state from HBM ("inputs larger than
 L2").
 
@@ -320,7 +320,7 @@ def bind_near_gpu(torch, index):
 class Workload:
     """M independent worlds of one config on this rank's GPU, stepped round-robin."""
 
-    def __init__(self, torch, E, name, cfg, envs, dev, rank, overlap, K, seed_base=0):
+    def __init__(self, torch, E, name, cfg, envs, dev, rank, overlap, K, seed_base=0, worlds=0):
         from rsoccer_b200 import _lib
         self.torch, self.E, self.name, self.cfg, self.N, self.dev = torch, E, name, cfg, envs, dev
         self.task = cfg["task"]
@@ -328,6 +328,8 @@ class Workload:
         # that a replay continues the rotation where the previous one stopped: M is the first count that keeps it short
         m0 = max(2, int(math.ceil(2.4 * L2_BYTES / (envs * cfg["alg"]))))
         self.M = next((m for m in range(m0, m0 + 4 * K + 1) if K * m // math.gcd(K, m) <= 4096), m0)
+        if worlds:
+            self.M = worlds          # e.g. 1: one world stepped again and again (state stays in L2; a true dependency chain)
         self.G = K * self.M // math.gcd(K, self.M)
         self.worlds, self.acts, self.outs = [], [], []
         gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
@@ -575,7 +577,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="vss65536", choices=sorted(CONFIGS))
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU of the main config")
-    ap.add_argument("--overlap", type=int, default=int(os.environ.get("RS_BENCH_OVERLAP", "1")), choices=[0, 1, 2],
+    ap.add_argument("--overlap", type=int, default=int(os.environ.get("RS_BENCH_OVERLAP", "3")), choices=[0, 1, 2, 3],
                     help="RS_OPT_STEP_OVERLAP of the timed worlds (include/rsoccer_b200.h)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -626,6 +628,21 @@ def main():
             wl.set_overlap(args.overlap)
         if world > 1 and cfg["task"] == "vss":
             extras["gather"] = gather_bench(torch, dist, wl, stream, dev, world)
+        if cfg["task"] == "vss":
+            # ONE world stepped again and again: step k+1 of a tile really waits for step k of that tile
+            # (state L2 resident -- this is a latency figure, not an HBM one; mode 2: the 7-CTA build)
+            w1 = Workload(torch, E, args.config, cfg, envs, dev, rank, 2, K, seed_base=9, worlds=1)
+            rc = measure(torch, dist, w1, K, W, args.min_ms / 2, stream, world, dev, e2e_steps=0)
+            w1.set_overlap(0)
+            rs = measure(torch, dist, w1, K, W, args.min_ms / 2, stream, world, dev, settle=False, e2e_steps=0)
+            extras["single_world"] = {
+                "what": "one %d-env world stepped back to back (no rotation: state stays in the 126 MB L2, every step "
+                        "depends on the previous one)" % envs,
+                "overlap2_ms_per_step": rc["ms_per_step"], "serialized_ms_per_step": rs["ms_per_step"],
+                "overlap2_value": envs * world / (rc["ms_per_step"] * 1e-3),
+                "serialized_value": envs * world / (rs["ms_per_step"] * 1e-3)}
+            w1.close()
+            del w1
     wl.close()
     del wl
     torch.cuda.empty_cache()
@@ -665,7 +682,11 @@ def main():
         cpu = cpu_baseline_run(cfg["task"], _host_threads(), args.cpu_seconds)
         modes = {0: "every step begins with a grid-wide wait on its predecessor (programmatic dependent launch hides the launch latency only)",
                  1: "RS_OPT_STEP_OVERLAP=1: steps synchronise per 32-match tile on the world state and grid-wide before reading the action buffer",
-                 2: "RS_OPT_STEP_OVERLAP=2: steps synchronise per 32-match tile only (fixed action buffers)"}
+                 2: "RS_OPT_STEP_OVERLAP=2: steps synchronise per 32-match tile only (fixed action buffers)",
+                 3: "RS_OPT_STEP_OVERLAP=3: steps synchronise per 32-match tile only (fixed action buffers) and the step kernel is "
+                    "built for 11 resident CTAs per SM; consecutive launches belong to different worlds of the rotation, so they "
+                    "are independent and overlap freely -- see `serialized` (grid-wide wait between steps) and `single_world` "
+                    "(one world stepped again and again: a true dependency chain) for the other two regimes"}
         line = {
             "metric": METRIC, "value": main_sum["value"], "unit": UNIT, "n_gpus": world, "steps": K,
             "repeats": main_sum["repeats"], "warmup": W, "ms_per_step": main_sum["ms_per_step"],

@@ -142,6 +142,9 @@ int rs_sync_t(rs_world *w, void *stream);
  *      d_normals were completely written before the PREVIOUS step launch of this world was
  *      enqueued (fixed or pre-generated action buffers, action repeat).  Any other work
  *      enqueued between two steps (a policy kernel, a copy) serialises them as usual.
+ *   3  as 2, with the step kernel built for 11 instead of 7 resident CTAs per SM: for several
+ *      worlds stepped round-robin on one stream (consecutive launches are then independent
+ *      and fill the GPU together); slower than 2 when one world is stepped again and again.
  * Whoever writes the state buffer behind the library's back (through the zero-copy views)
  * sets the option again afterwards: the next step then starts with a grid-wide wait.
  * RS_OPT_PDL (default 1): launch step kernels with programmatic stream serialization.

@@ -44,7 +44,7 @@ struct VssStepArgs {
     // step-to-step overlap (rs_device.cuh, tile_acquire): one flag word per 32-match tile + one error
     // word behind them, or null.  chain = 0: grid-wide wait first (griddepcontrol.wait), 1: per-tile wait
     // for the state, grid-wide wait before the first read of a caller buffer (actions, normals),
-    // 2: per-tile wait only (the caller vouches for its buffers, RS_OPT_STEP_OVERLAP = 2)
+    // 2 / 3: per-tile wait only (the caller vouches for its buffers, RS_OPT_STEP_OVERLAP = 2 / 3)
     uint32_t *flags;
     int chain;
 };
@@ -54,10 +54,12 @@ struct VssStepArgs {
 // auto-reset and the observation tile (leaves through a TMA bulk store).
 //
 // DENSE: the same source compiled for 11 resident CTAs per SM (80 registers instead of 114, no spills, same
-// instruction count).  A launch that overlaps its predecessor (A.chain != 0) wants as many CTAs of the NEXT
-// step resident as registers allow (65 536 matches at 8 worlds: 12.2 -> 10.5 us per step); a launch that
-// starts on an empty GPU wants its 1 024 CTAs spread over all 148 SMs, 7 per SM -- with DENSE the block
-// scheduler packs them 11 per SM onto 93 SMs (15.8 -> 19.5 us), so the host picks per launch.
+// instruction count).  When several worlds are stepped round-robin on one stream (RS_OPT_STEP_OVERLAP = 3)
+// consecutive launches are independent and as many CTAs of the NEXT step as registers allow should be
+// resident (65 536 matches, 8 worlds: 10.7 -> 9.2 us per step).  A launch that starts on an empty GPU, or
+// behind a true dependency (one world stepped again and again), wants its 1 024 CTAs spread over all 148
+// SMs, 7 per SM -- with DENSE the block scheduler packs them 11 per SM onto 93 SMs (15.8 -> 19.5 us
+// serialised, 12.8 -> 16.6 us chained on one world), so the caller chooses.
 template <int NB, int NY, int BS, int F0 /* 0: run-time physics constants.  1: VssF0's, immediates instead of
           constant-bank loads.  2: VssF0P, the same with the packed fp32x2 instruction forms (rs_device.cuh) */,
           bool DENSE = false>
@@ -77,16 +79,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
-    uint32_t *const tile_flag = A.flags ? A.flags + (w0 >> 5) : nullptr;
-    if (A.chain == 0) pdl_wait();
-    if (tile_flag) {
-        tile_acquire(tile_flag, A.flags + ((S.np + 31) >> 5));
-        // the CTA's trigger must not fire before ALL its warps hold their tiles (a CTA counts as triggered
-        // once any of its threads has executed launch_dependents): otherwise step k+2 could start and
-        // wait for a tile that step k+1 has not taken yet
-        if (BS > 32) __syncthreads();
-    }
-    pdl_release();
+    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
     if (e < S.n) {
         // ---- every global load of the step is issued first: the step counter ahead of the state,
         // so that it is not queued behind 100 KB of requests per SM and Philox can start at once
@@ -104,7 +97,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 #pragma unroll
         for (int r = 1; r < R; ++r) ou[r - 1] = __ldcg(S.ou + (size_t)(r - 1) * S.np + e);
         float2 act = make_float2(0.0f, 0.0f);
-        if (A.chain != 1) act = A.actions[e];
+        if (A.chain != 1) act = __ldcg(A.actions + e);      // around L1, like the state: read once, and never stale
 
         // ---- ... and the OU noise (Philox + Box-Muller, ~15 % of the instructions, needs
         // only the env id and the step counter) is computed while they are in flight
@@ -112,7 +105,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         if (A.normals) {
             if (A.chain == 1) pdl_wait();
 #pragma unroll
-            for (int k = 0; k < NZ; ++k) z[k] = A.normals[(size_t)e * NZ + k];
+            for (int k = 0; k < NZ; ++k) z[k] = __ldcg(A.normals + (size_t)e * NZ + k);
         } else {
             // Philox stream (global env id, t, OU): Box-Muller on consecutive u32 pairs
             const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
@@ -133,7 +126,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 
         // caller buffers are read only after the predecessor grid has completed (chain 1: the state
         // loads and the noise above already ran under its tail)
-        if (A.chain == 1) { pdl_wait(); act = A.actions[e]; }
+        if (A.chain == 1) { pdl_wait(); act = __ldcg(A.actions + e); }
 
         // ---- _get_commands, vss_gym.py:119-142
         Drive<R> d;
@@ -235,7 +228,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 #pragma unroll
         for (int i = 0; i < NOBS / 4; ++i) { const int k = i * 32 + (tid & 31); if (k < total) dst[k] = src[k]; }
     }
-    if (tile_flag) tile_release(tile_flag);
+    step_end(tile_flag);
 }
 
 
@@ -264,22 +257,21 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     const int p = is_ou ? b - 2 : 0;                           // OU process of this lane (blue 0 is the agent)
     const uint32_t gid = A.env_offset + (uint32_t)ec;
 
-    pdl_wait();
-    pdl_release();
+    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
     // ---- loads first: own body, own task word, own action source
     LaneBody s;
     lanes_load<L>(S, R, b, ec, s);
-    const uint32_t aux = S.aux[(size_t)b * S.np + ec];
+    const uint32_t aux = __ldcg(S.aux + (size_t)b * S.np + ec);
     float2 a = make_float2(0.0f, 0.0f);
-    if (b == 1) a = A.actions[ec];
-    if (is_ou) a = S.ou[(size_t)p * S.np + ec];
+    if (b == 1) a = __ldcg(A.actions + ec);
+    if (is_ou) a = __ldcg(S.ou + (size_t)p * S.np + ec);
     const uint32_t t_now = step_counter_read<RS_CTR_GROUP * L>(A.ctr, ec);
 
     // ---- OU noise under the load latency: normals (2p, 2p + 1) are Box-Muller of the
     // u32 pair (p & 1) of Philox call p / 2 of the (global env id, t, OU) stream
     float z0 = 0.0f, z1 = 0.0f;
     if (A.normals) {
-        if (is_ou) { z0 = A.normals[(size_t)ec * NZ + 2 * p]; z1 = A.normals[(size_t)ec * NZ + 2 * p + 1]; }
+        if (is_ou) { z0 = __ldcg(A.normals + (size_t)ec * NZ + 2 * p); z1 = __ldcg(A.normals + (size_t)ec * NZ + 2 * p + 1); }
     } else {
         const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
         const uint4 u = philox4x32_10(make_uint4(gid, t_now, RS_STREAM_OU, (uint32_t)(p >> 1)), key);
@@ -374,7 +366,8 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
         }
     }
     if (valid) step_counter_bump<RS_CTR_GROUP * L>(A.ctr, e, t_now);
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS, tile_flag == nullptr);
+    step_end(tile_flag);
 }
 
 struct SslStepArgs {
@@ -386,6 +379,8 @@ struct SslStepArgs {
     uint64_t seed;
     uint32_t *ctr;
     uint32_t env_offset;
+    uint32_t *flags;         // step-to-step overlap, as in VssStepArgs (chain 0 or 2 here)
+    int chain;
 };
 
 // SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step
@@ -400,21 +395,20 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
-    pdl_wait();
-    pdl_release();
+    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
     if (e < S.n) {
         Scene<R> s;
         load_scene<R>(P, S, e, s);
-        int steps = S.steps[e] & 0xFFFFFF;
+        int steps = __ldcg(S.steps + e) & 0xFFFFFF;
         float info[RS_SSL_INFO];
 #pragma unroll
-        for (int i = 0; i < RS_SSL_INFO; ++i) info[i] = steps == 0 ? 0.0f : S.info[(size_t)i * S.np + e];
+        for (int i = 0; i < RS_SSL_INFO; ++i) info[i] = steps == 0 ? 0.0f : __ldcg(S.info + (size_t)i * S.np + e);
         steps += 1;
         const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
         // ---- _get_commands + convert_actions, static_defenders.py:114-148
         float a[RS_SSL_ACT];
 #pragma unroll
-        for (int i = 0; i < RS_SSL_ACT; ++i) a[i] = A.actions[(size_t)e * RS_SSL_ACT + i];
+        for (int i = 0; i < RS_SSL_ACT; ++i) a[i] = __ldcg(A.actions + (size_t)e * RS_SSL_ACT + i);
         const float max_v = 2.5f, max_w = 10.0f, kick_speed = 5.0f;
         float cmd[8];
         {
@@ -511,7 +505,8 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         ssl_obs<NB, NY>(P, s, tile + tid * NOBS);
         step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
     }
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS, tile_flag == nullptr);
+    step_end(tile_flag);
 }
 
 // SSLHWDribblingEnv.step (TASK 3: 1 blue + 4 yellow, dribbling.py) and SSLPassEnduranceEnv.step
@@ -520,27 +515,22 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
 // info[0..1] of pass endurance = reward_shaping_total {reversed_dist, ball_grad}
 // (pass_endurance.py:113-114).  pass_endurance.py never increments holding_steps (:56, :92,
 // :121), so its `> 15` test never fires and is not restated.
-template <int TASK, int NB, int NY, int BS>
-__global__ void __launch_bounds__(BS)
-k_ssl_hw_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
+template <int TASK, int NB, int NY>
+__device__ __forceinline__ void ssl_hw_env_step_match(const DevParams &P, const StatePtrs &S, const SslStepArgs &A,
+                                                      const int e, const unsigned live) {
     constexpr int R = NB + NY;
     constexpr bool DRIB = TASK == RS_TASK_SSL_DRIBBLING;
     constexpr int NACT = DRIB ? RS_DRIB_ACT : RS_PASS_ACT, NOBS = DRIB ? RS_DRIB_OBS : RS_PASS_OBS;
-    const int e = blockIdx.x * BS + threadIdx.x;
-    const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
-    pdl_wait();
-    pdl_release();
-    if (e >= S.n) return;
     Scene<R> s;
     load_scene<R>(P, S, e, s);
-    int steps = S.steps[e] & 0xFFFFFF;
-    float counter = steps == 0 ? 0.0f : S.prev[e];
-    float info0 = steps == 0 ? 0.0f : S.info[e], info1 = steps == 0 ? 0.0f : S.info[(size_t)S.np + e];
+    int steps = __ldcg(S.steps + e) & 0xFFFFFF;
+    float counter = steps == 0 ? 0.0f : __ldcg(S.prev + e);
+    float info0 = steps == 0 ? 0.0f : __ldcg(S.info + e), info1 = steps == 0 ? 0.0f : __ldcg(S.info + (size_t)S.np + e);
     steps += 1;
     const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
     float a[NACT];
 #pragma unroll
-    for (int i = 0; i < NACT; ++i) a[i] = A.actions[(size_t)e * NACT + i];
+    for (int i = 0; i < NACT; ++i) a[i] = __ldcg(A.actions + (size_t)e * NACT + i);
     const float max_v = 2.5f, max_w = 10.0f, max_kick_x = 5.0f;
     float cmd[R][8];
 #pragma unroll
@@ -649,6 +639,15 @@ k_ssl_hw_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const 
     S.prev[e] = counter;
     step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
 }
+template <int TASK, int NB, int NY, int BS>
+__global__ void __launch_bounds__(BS)
+k_ssl_hw_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
+    const int e = blockIdx.x * BS + threadIdx.x;
+    const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
+    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
+    if (e < S.n) ssl_hw_env_step_match<TASK, NB, NY>(P, S, A, e, live);
+    step_end(tile_flag);
+}
 
 
 // SSLHWStaticDefendersEnv.step / SSLContestedPossessionEnv.step, one lane per BODY
@@ -673,19 +672,18 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     const LaneGroup<L> g;
     const bool is_robot = b >= 1 && b <= R;
 
-    pdl_wait();
-    pdl_release();
+    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
     LaneBody s;
     lanes_load<L>(S, R, b, ec, s);
     uint32_t aux[KW];
 #pragma unroll
     for (int k = 0; k < KW; ++k) {
         const int w = b + k * L;                               // (word 0, the VSS ball potential, is unused here)
-        aux[k] = (w < NW && w != RS_AUX_PREV) ? S.aux[(size_t)w * S.np + ec] : 0u;
+        aux[k] = (w < NW && w != RS_AUX_PREV) ? __ldcg(S.aux + (size_t)w * S.np + ec) : 0u;
     }
     float a[RS_SSL_ACT];
 #pragma unroll
-    for (int i = 0; i < RS_SSL_ACT; ++i) a[i] = b == 1 ? A.actions[(size_t)ec * RS_SSL_ACT + i] : 0.0f;
+    for (int i = 0; i < RS_SSL_ACT; ++i) a[i] = b == 1 ? __ldcg(A.actions + (size_t)ec * RS_SSL_ACT + i) : 0.0f;
     const uint32_t t_now = step_counter_read<RS_CTR_GROUP * L>(A.ctr, ec);
 
     // ---- _get_commands + convert_actions, static_defenders.py:114-148 (blue 0; the other
@@ -794,7 +792,8 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
         }
     }
     if (valid) step_counter_bump<RS_CTR_GROUP * L>(A.ctr, e, t_now);
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS, tile_flag == nullptr);
+    step_end(tile_flag);
 }
 
 // simulator.step(cmds), one lane per BODY: any (kind, R <= 31) with L = 2^k >= R + 1
@@ -1042,10 +1041,11 @@ struct rs_world {
     bool pdl;                // step kernels are launched with programmatic stream serialization (RS_PDL=0 turns it off)
     bool host_copy_actions;  // RS_HOST_COPY_ACTIONS=1: stage pinned host actions with a copy instead of reading them in place
     // step-to-step overlap (RS_OPT_STEP_OVERLAP; rs_device.cuh, tile_acquire)
-    int overlap;             // 0 off, 1 state through tile flags + grid wait before caller buffers, 2 tile flags only
-    uint32_t *d_flags;       // [np / 32] tile flags + 1 error word (library-owned)
+    int overlap;             // 0 off, 1 state through tile flags + grid wait before caller buffers, 2 tile flags only, 3 = 2 + dense CTAs
+    uint32_t *d_flags;       // word 0: error counter; words 1 .. np: tile flags, one per warp of a step kernel (library-owned)
     bool chain_ok;           // the previous launch that touched the state was a flag-protocol step ...
-    cudaStream_t chain_stream;   // ... on this stream
+    cudaStream_t chain_stream;   // ... on this stream ...
+    int chain_family;        // ... of this kernel family (= tile mapping; a different family starts with a grid-wide wait)
     // scratch for the *_host entry points (library owned)
     float *s_actions, *s_obs, *s_reward;
     uint8_t *s_done, *s_trunc;
@@ -1285,9 +1285,9 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     if (const char *nv = getenv("RS_NO_PRESET")) { if (atoi(nv) == 1) w->f0 = 0; }
     if (const char *bs = getenv("RS_BLOCK")) { const int b = atoi(bs); if (b == 32 || b == 64 || b == 128 || b == 256) w->block = b; }
     w->overlap = 0;
-    if (const char *ov = getenv("RS_STEP_OVERLAP")) { const int v = atoi(ov); if (v >= 0 && v <= 2) w->overlap = v; }
+    if (const char *ov = getenv("RS_STEP_OVERLAP")) { const int v = atoi(ov); if (v >= 0 && v <= 3) w->overlap = v; }
     w->n_ctr = w->np / RS_CTR_GROUP;
-    const size_t flag_bytes = ((size_t)w->np / 32 + 1) * sizeof(uint32_t);
+    const size_t flag_bytes = ((size_t)w->np + 1) * sizeof(uint32_t);
     if (cudaMalloc(&w->d_ctr, w->n_ctr * sizeof(uint32_t)) != cudaSuccess || cudaMemset(w->d_ctr, 0, w->n_ctr * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&w->d_flags, flag_bytes) != cudaSuccess || cudaMemset(w->d_flags, 0, flag_bytes) != cudaSuccess) {
         cudaFree(w->d_ctr); cudaFree(w->d_flags);
@@ -1460,7 +1460,7 @@ int rs_set_option(rs_world *w, int option, int64_t value) {
     if (!w) return fail(RS_E_INVALID, "rs_set_option: null world");
     switch (option) {
         case RS_OPT_STEP_OVERLAP:
-            if (value < 0 || value > 2) return fail(RS_E_INVALID, "rs_set_option: RS_OPT_STEP_OVERLAP takes 0, 1 or 2");
+            if (value < 0 || value > 3) return fail(RS_E_INVALID, "rs_set_option: RS_OPT_STEP_OVERLAP takes 0, 1, 2 or 3");
             w->overlap = (int)value; w->chain_ok = false;     // also: "the state was written behind the library's back"
             return RS_OK;
         case RS_OPT_PDL:
@@ -1478,7 +1478,7 @@ int rs_get_option(const rs_world *w, int option, int64_t *value, void *stream) {
         case RS_OPT_OVERLAP_ERRORS: {
             ON_DEVICE(w, "rs_get_option");
             uint32_t e = 0;
-            CUDA_TRY(cudaMemcpyAsync(&e, w->d_flags + w->np / 32, sizeof(e), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+            CUDA_TRY(cudaMemcpyAsync(&e, w->d_flags, sizeof(e), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
             CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
             *value = e;
             return RS_OK;
@@ -1538,30 +1538,37 @@ int rs_task_reset(rs_world *w, int task, const uint8_t *d_mask, float *d_obs, vo
     return RS_OK;
 }
 
+// Step-to-step overlap, host side: a launch takes part in the tile-flag protocol whenever the option is on,
+// and may skip the grid-wide wait (chain != 0) when the launch before it -- same world, same stream, same
+// kernel family, i.e. same tile mapping -- took part too.  Mode 1 (grid-wide wait before the caller's buffers
+// are read) exists in the lane-per-match VSS-v0 kernel only; every other kernel treats it as 0.
+static void chain_setup(rs_world *w, int family, bool has_mode1, cudaStream_t st, uint32_t *&flags, int &chain) {
+    flags = nullptr; chain = 0;
+    if (w->overlap) {
+        flags = w->d_flags;
+        if (w->pdl && w->chain_ok && w->chain_stream == st && w->chain_family == family && (w->overlap != 1 || has_mode1))
+            chain = w->overlap;
+    }
+    w->chain_ok = w->overlap != 0; w->chain_stream = st; w->chain_family = family;
+}
+
 // One launch of VSSEnv.step over the S.n matches S / A point at.
 static void launch_vss(rs_world *w, VssStepArgs &A, const StatePtrs &S, cudaStream_t st) {
     const int n = S.n;
-    A.flags = nullptr; A.chain = 0;
     if (use_lane_per_body(w, true)) {
-        w->chain_ok = false;
+        chain_setup(w, 100 + w->lane_block, false, st, A.flags, A.chain);
         if (w->lane_block == 256) launch_step_kernel(w, k_vss_env_step_lanes<256>, (n + 31) / 32, 256, st, w->dp, S, A);
         else if (w->lane_block == 64) launch_step_kernel(w, k_vss_env_step_lanes<64>, (n + 7) / 8, 64, st, w->dp, S, A);
         else if (w->f0) launch_step_kernel(w, k_vss_env_step_lanes<128, true>, (n + 15) / 16, 128, st, w->dp, S, A);
         else launch_step_kernel(w, k_vss_env_step_lanes<128>, (n + 15) / 16, 128, st, w->dp, S, A);
         return;
     }
-    // step-to-step overlap: this launch takes part in the tile-flag protocol when the option is on, and may skip
-    // the grid-wide wait when the launch before it (same world, same stream) took part too
-    if (w->overlap) {
-        A.flags = w->d_flags;
-        if (w->pdl && w->chain_ok && w->chain_stream == st) A.chain = w->overlap;
-    }
-    w->chain_ok = w->overlap != 0; w->chain_stream = st;
+    chain_setup(w, 1, true, st, A.flags, A.chain);          // every lane-per-match build has the same tiles: 32 matches
     if (w->f0 && use_packed(w)) switch (w->block) {
         case 32: launch_step_kernel(w, k_vss_env_step<3, 3, 32, 2>, (n + 31) / 32, 32, st, w->dp, S, A); break;
         case 128: launch_step_kernel(w, k_vss_env_step<3, 3, 128, 2>, (n + 127) / 128, 128, st, w->dp, S, A); break;
         default:
-            if (A.chain) launch_step_kernel(w, k_vss_env_step<3, 3, 64, 2, true>, (n + 63) / 64, 64, st, w->dp, S, A);
+            if (A.chain == 3) launch_step_kernel(w, k_vss_env_step<3, 3, 64, 2, true>, (n + 63) / 64, 64, st, w->dp, S, A);
             else launch_step_kernel(w, k_vss_env_step<3, 3, 64, 2>, (n + 63) / 64, 64, st, w->dp, S, A);
             break;
     } else if (w->f0) {
@@ -1610,10 +1617,13 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
     cudaStream_t st = (cudaStream_t)stream;
     const int rc = push_t(w, st);
     if (rc) return rc;
-    w->chain_ok = false;
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     const StatePtrs S = state_ptrs(w);
     const int g64 = (w->n + 63) / 64, g128 = (w->n + 127) / 128;
+    // kernel family = tile mapping: lane per match (32 matches per warp) or lane per body (by CTA size: the
+    // lanes per match are fixed by the world)
+    chain_setup(w, (task == RS_TASK_SSL_DRIBBLING_V0 || task == RS_TASK_SSL_PASS_ENDURANCE_V0 || !use_lane_per_body(w, true))
+                       ? 1 : 100 + w->lane_block, false, st, A.flags, A.chain);
     if (task == RS_TASK_SSL_DRIBBLING_V0) {
         launch_step_kernel(w, k_ssl_hw_env_step<RS_TASK_SSL_DRIBBLING, 1, 4, 64>, g64, 64, st, w->dp, S, A);
     } else if (task == RS_TASK_SSL_PASS_ENDURANCE_V0) {

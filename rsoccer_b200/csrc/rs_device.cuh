@@ -825,11 +825,13 @@ __device__ __forceinline__ void store_scene(const DevParams &P, const StatePtrs 
 // bulk copy (cp.async.bulk.global.shared::cta, SASS UBLKCP) -- no CTA-wide barrier --
 // when the span is 16-byte granular, else as a coalesced warp copy.
 // gdst / stile point at row 0 of the CALLING WARP; rows = valid rows of this warp.
-__device__ __forceinline__ void warp_tile_store(float *gdst, const float *stile, int rows, int row_floats) {
+// bulk = false (launches that take part in the step-overlap protocol): always the warp copy -- the tile
+// hand-over at the end of the kernel orders generic-proxy stores (fence + flag), not the async proxy's.
+__device__ __forceinline__ void warp_tile_store(float *gdst, const float *stile, int rows, int row_floats, const bool bulk = true) {
     const uint32_t bytes = (uint32_t)rows * (uint32_t)row_floats * 4u;
     const int lane = threadIdx.x & 31;
     if (rows <= 0) return;
-    if ((bytes & 15u) == 0u && ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0u)) {
+    if (bulk && (bytes & 15u) == 0u && ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0u)) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -896,31 +898,36 @@ __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.lau
 // step k+1 depends only on match i at step k.  With RS_OPT_STEP_OVERLAP the dependency is
 // tracked per 32-match tile (= one warp of the lane-per-match kernels) through one flag word
 // per tile in device memory (library owned, 0 = ready, 1 = a step is working on the tile):
-//   start of a warp:  lane 0 spins (ld.acquire.gpu) until its tile is ready, marks it busy with
-//                     an atomic exchange (performed at L2 before the warp goes on), then the
-//                     warp calls griddepcontrol.launch_dependents -- so step k+2 cannot launch
-//                     before every tile of step k has been handed to step k+1;
+//   start of a warp:  lane 0 takes the tile with an atomic compare-and-swap 0 -> 1 (performed at
+//                     L2), spinning while a previous step still holds it; then the CTA calls
+//                     griddepcontrol.launch_dependents -- so step k+2 cannot launch before
+//                     every tile of step k has been handed to step k+1;
 //   end of a warp:    __syncwarp, lane 0: __threadfence (cumulative: covers the stores of the
 //                     whole warp), then marks the tile ready.
+// Visibility.  The producer's fence makes its stores visible at L2 before the flag flips.  The
+// consumer reads the flag with an L2 atomic and everything a predecessor may have written --
+// state, task words, step counter -- with loads that go around L1 (ld.global.cg, issued only after
+// the atomic has returned: the loop exit depends on its value), so no stale line of this SM's
+// non-coherent L1 can be observed and no L1 invalidation is needed.  (An ld.acquire.gpu here
+// costs a CCTL.IVALL -- the whole L1 -- plus a second L2 round trip before the first state load
+// can issue: 7 % of the warp time at 1 M matches, profiles/r2_overlap.txt.)
 // No deadlock: a programmatic launch starts only after EVERY CTA of the predecessor has
 // executed launch_dependents, i.e. is resident, so a spinning warp always waits for a running
-// one.  The spin is bounded anyway (RS_SPIN_LIMIT polls, then the tile error word is set and the
+// one.  The spin is bounded anyway (RS_SPIN_LIMIT polls, then the error word is bumped and the
 // warp goes on): a protocol error must not hang the GPU.
 #ifndef RS_SPIN_LIMIT
-#define RS_SPIN_LIMIT (1 << 20)
+#define RS_SPIN_LIMIT (1 << 19)
 #endif
 __device__ __forceinline__ void tile_acquire(uint32_t *flag, uint32_t *err) {
     if ((threadIdx.x & 31) == 0) {
-        uint32_t v;
+        uint32_t old;
         int spins = 0;
         for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if (v == 0u || ++spins > RS_SPIN_LIMIT) break;
-            __nanosleep(40);
+            asm volatile("atom.relaxed.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(flag), "r"(0u), "r"(1u) : "memory");
+            if (old == 0u || ++spins > RS_SPIN_LIMIT) break;
+            __nanosleep(32);
         }
-        uint32_t old;
-        asm volatile("atom.exch.acquire.gpu.global.b32 %0, [%1], %2;" : "=r"(old) : "l"(flag), "r"(1u) : "memory");
-        if (old != 0u) atomicAdd(err, 1u);     // timed out, or two steps of one world on different streams
+        if (old != 0u) atomicAdd(err, 1u);     // timed out: two steps of one world on different streams, or a dead predecessor
     }
     __syncwarp();
 }
@@ -931,3 +938,25 @@ __device__ __forceinline__ void tile_release(uint32_t *flag) {
         asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(0u) : "memory");
     }
 }
+// Start of every task step kernel.  flags: word 0 = error counter, word 1 + i = tile i, where a tile is
+// what one WARP of this kernel works on (32 matches in the lane-per-match kernels, 32 / L matches in
+// the lane-per-body kernels) -- the host chains two launches only if they run the same kernel.
+//   chain == 0: grid-wide wait first (griddepcontrol.wait), then take the tile (always free)
+//   chain != 0: no grid-wide wait here, the tile is the dependency
+// Returns this warp's tile (null without flags) for step_end.
+template <int BS>
+__device__ __forceinline__ uint32_t *step_begin(uint32_t *flags, const int chain) {
+    uint32_t *tile = nullptr;
+    if (chain == 0) pdl_wait();
+    if (flags) {
+        tile = flags + 1 + ((blockIdx.x * BS + threadIdx.x) >> 5);
+        tile_acquire(tile, flags);
+        // the CTA's trigger must not fire before ALL its warps hold their tiles (a CTA counts as triggered
+        // once any of its threads has executed launch_dependents): otherwise step k+2 could start and
+        // wait for a tile that step k+1 has not taken yet
+        if (BS > 32) __syncthreads();
+    }
+    pdl_release();
+    return tile;
+}
+__device__ __forceinline__ void step_end(uint32_t *tile) { if (tile) tile_release(tile); }

@@ -222,11 +222,11 @@ template <int L>
 __device__ __forceinline__ void lanes_load(const StatePtrs &S, const int R, const int b, const int e, LaneBody &s) {
     s.x = s.y = s.vx = s.vy = s.th = s.om = 0.0f;
     if (b <= R) {
-        const float4 q = S.body[(size_t)b * S.np + e];
+        const float4 q = __ldcg(S.body + (size_t)b * S.np + e);      // around L1, as in load_scene (rs_device.cuh)
         s.x = q.x; s.y = q.y; s.vx = q.z; s.vy = q.w;
     }
     if (b >= 1 && b <= R) {
-        const float2 a = S.ang[(size_t)(b - 1) * S.np + e];
+        const float2 a = __ldcg(S.ang + (size_t)(b - 1) * S.np + e);
         s.th = a.x; s.om = a.y;
     }
 }

@@ -107,7 +107,7 @@ class BatchedWorld:
 
     @t.setter
     def t(self, v):
-        self.L.rs_set_t(self.h, int(v))
+        _lib.check(self.L.rs_set_t(self.h, int(v)), "rs_set_t")
 
     def sync_t(self):
         """Read the device-resident step counter back (needed after CUDA-graph replays)."""

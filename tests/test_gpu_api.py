@@ -328,8 +328,8 @@ def test_step_overlap_modes_are_bit_identical(_engine_module, monkeypatch, n):
     E, L = _engine_module, _lib_consts()
     monkeypatch.setenv("RS_PER_MATCH", "1")
     monkeypatch.delenv("RS_STEP_OVERLAP", raising=False)
-    ws = _twin_worlds(E, n, 11, (0, 1, 2))
-    assert [w.get_option(L.OPT_STEP_OVERLAP) for w in ws] == [0, 1, 2]
+    ws = _twin_worlds(E, n, 11, (0, 1, 2, 3))
+    assert [w.get_option(L.OPT_STEP_OVERLAP) for w in ws] == [0, 1, 2, 3]
     a = (torch.rand(n, 2, device="cuda") * 2 - 1)
     outs = [w.alloc_outputs(E.TASK_VSS_V0) for w in ws]
     s = torch.cuda.Stream()
@@ -353,6 +353,83 @@ def test_step_overlap_modes_are_bit_identical(_engine_module, monkeypatch, n):
         assert f[2] == finals[0][2]
         assert torch.equal(f[0], finals[0][0])
         assert all(torch.equal(x, y) for x, y in zip(f[1], finals[0][1]))
+
+
+@pytest.mark.parametrize("task,per_match,n", [("vss", 0, 4096), ("sd", 0, 4096), ("sd", 1, 20000), ("cp", 0, 5000), ("cp", 1, 16384),
+                                              ("drib", 1, 3000), ("pass", 1, 3000)])
+def test_step_overlap_in_every_task_kernel(_engine_module, monkeypatch, task, per_match, n):
+    """the tile protocol in the other step kernels (one lane per body: a tile is the 32 / L matches of a warp; the
+    SSL tasks): chained launches from a replayed graph against the serialised twin, bit for bit"""
+    E, L = _engine_module, _lib_consts()
+    monkeypatch.setenv("RS_PER_MATCH", str(per_match))
+    monkeypatch.delenv("RS_STEP_OVERLAP", raising=False)
+    spec = {"vss": (0, 0, 3, 3, E.TASK_VSS_V0, 2), "sd": (1, 2, 1, 6, E.TASK_SSL_STATIC_DEFENDERS_V0, 5),
+            "cp": (1, 2, 1, 1, E.TASK_SSL_CONTESTED_POSSESSION_V0, 5), "drib": (1, 2, 1, 4, E.TASK_SSL_DRIBBLING_V0, 4),
+            "pass": (1, 2, 2, 0, E.TASK_SSL_PASS_ENDURANCE_V0, 3)}[task]
+    kind, ft, nb, ny, tid, ad = spec
+    a = torch.rand(n, ad, device="cuda") * 2 - 1
+    s = torch.cuda.Stream()
+    finals = []
+    for mode in (0, 2):
+        w = E.BatchedWorld(kind, ft, nb, ny, 25, n, seed=31)
+        w.set_option(L.OPT_STEP_OVERLAP, mode)
+        w.task_reset(tid)
+        out = w.alloc_outputs(tid)
+
+        def step():
+            if task == "vss":
+                w.vss_env_step(a, out=out, max_steps=60)
+            else:
+                w.ssl_env_step(tid, a, out=out, max_steps=60)
+        with torch.cuda.stream(s):
+            for _ in range(20):
+                step()
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(20):
+                    step()
+            for _ in range(10):
+                g.replay()
+            s.synchronize()
+        assert w.get_option(L.OPT_OVERLAP_ERRORS) == 0
+        finals.append((w.state.clone(), [o.clone() for o in out]))
+    assert torch.equal(finals[0][0], finals[1][0])
+    assert all(torch.equal(x, y) for x, y in zip(finals[0][1], finals[1][1]))
+
+
+def test_step_overlap_with_worlds_in_rotation(_engine_module, monkeypatch):
+    """the benchmark's pattern: several worlds stepped round-robin on one stream from one captured graph, so that
+    consecutive launches are independent and overlap freely (mode 3: the dense build); every world must end
+    exactly where its serialised twin ends"""
+    E, L = _engine_module, _lib_consts()
+    monkeypatch.setenv("RS_PER_MATCH", "1")
+    n, M = 40000, 3
+    a = [(torch.rand(n, 2, device="cuda") * 2 - 1) for _ in range(M)]
+    s = torch.cuda.Stream()
+    finals = []
+    for mode in (0, 3):
+        ws = []
+        for m in range(M):
+            w = E.BatchedWorld(0, 0, 3, 3, 25, n, seed=21, env_offset=m * n)
+            w.set_option(L.OPT_STEP_OVERLAP, mode)
+            w.task_reset(E.TASK_VSS_V0)
+            ws.append(w)
+        outs = [w.alloc_outputs(E.TASK_VSS_V0) for w in ws]
+        with torch.cuda.stream(s):
+            for i in range(3 * M):
+                ws[i % M].vss_env_step(a[i % M], out=outs[i % M], max_steps=50)
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for i in range(4 * M):
+                    ws[i % M].vss_env_step(a[i % M], out=outs[i % M], max_steps=50)
+            for _ in range(20):
+                g.replay()
+            s.synchronize()
+        assert all(w.get_option(L.OPT_OVERLAP_ERRORS) == 0 for w in ws)
+        finals.append([w.state.clone() for w in ws])
+    assert all(torch.equal(x, y) for x, y in zip(*finals))
 
 
 def test_step_overlap_survives_interleaved_calls(_engine_module, monkeypatch):
