@@ -388,7 +388,13 @@ template <int TASK, int NB, int NY, int BS>
 __global__ void __launch_bounds__(BS)
 k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
     constexpr int R = NB + NY, NOBS = 4 + 8 * NB + 2 * NY;
-    __shared__ __align__(128) float tile[BS * NOBS];
+    // one region per WARP, as in k_vss_env_step: contact scratch during the physics (worlds of >= 3 robots:
+    // per-lane resolve through shared memory, contacts_via_smem_ssl), then placement words, then its 32 obs rows
+    constexpr bool SCR = R >= 3;
+    constexpr int SCRATCH = SCR ? 2 * (R + 1) * 32 * 4 : 0, WF = 32 * NOBS > SCRATCH ? 32 * NOBS : SCRATCH;
+    __shared__ __align__(128) float smem[BS / 32][WF];
+    float *const wtile = smem[threadIdx.x >> 5];
+    float4 *const cq = reinterpret_cast<float4 *>(wtile) + (threadIdx.x & 31);
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * BS;
     const int e = e0 + tid;
@@ -433,7 +439,8 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         }
         const float lbx = s.bx, lby = s.by, lrx = s.x[0], lry = s.y[0];   // last_frame
 
-        physics_step<RS_KIND_SSL, R>(P, s, d, live);
+        if constexpr (SCR) physics_step<RS_KIND_SSL, R>(P, s, d, live, cq, cq + (R + 1) * 32, 32);
+        else physics_step<RS_KIND_SSL, R>(P, s, d, live);
 
         // ---- _calculate_reward_and_done, static_defenders.py:150-212 / contested_possession.py:136-208
         float rew = 0.0f; bool dn = false;
@@ -484,8 +491,9 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         } else if (A.auto_reset) {
             // warp-cooperative placement of the ending matches (see k_vss_env_step); the word buffer is
             // this warp's part of the observation tile, not yet written
-            uint32_t *const wbuf = reinterpret_cast<uint32_t *>(tile + (tid & ~31) * NOBS);
+            uint32_t *const wbuf = reinterpret_cast<uint32_t *>(wtile);
             static_assert(32 * NOBS >= 128, "128 placement words fit the warp's observation rows");
+            __syncwarp(live);      // the words overlay the other lanes' contact scratch
             unsigned need = __ballot_sync(live, dn || tr);
             while (need) {
                 const int src = __ffs((int)need) - 1;
@@ -501,11 +509,11 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         }
         store_scene<R>(P, S, e, s);
         S.steps[e] = steps;
-        __syncwarp(live);          // the rows below overlay the placement words an ending lane may still read
-        ssl_obs<NB, NY>(P, s, tile + tid * NOBS);
+        __syncwarp(live);          // the rows below overlay the scratch / the placement words an ending lane may still read
+        ssl_obs<NB, NY>(P, s, wtile + (tid & 31) * NOBS);
         step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
     }
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid & ~31) * NOBS, wrows, NOBS, tile_flag == nullptr);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, wtile, wrows, NOBS, tile_flag == nullptr);
     step_end(tile_flag);
 }
 
@@ -517,10 +525,11 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
 // :121), so its `> 15` test never fires and is not restated.
 template <int TASK, int NB, int NY>
 __device__ __forceinline__ void ssl_hw_env_step_match(const DevParams &P, const StatePtrs &S, const SslStepArgs &A,
-                                                      const int e, const unsigned live) {
+                                                      const int e, const unsigned live, float *const wtile) {
     constexpr int R = NB + NY;
     constexpr bool DRIB = TASK == RS_TASK_SSL_DRIBBLING;
     constexpr int NACT = DRIB ? RS_DRIB_ACT : RS_PASS_ACT, NOBS = DRIB ? RS_DRIB_OBS : RS_PASS_OBS;
+    float4 *const cq = reinterpret_cast<float4 *>(wtile) + (threadIdx.x & 31);
     Scene<R> s;
     load_scene<R>(P, S, e, s);
     int steps = __ldcg(S.steps + e) & 0xFFFFFF;
@@ -568,10 +577,13 @@ __device__ __forceinline__ void ssl_hw_env_step_match(const DevParams &P, const 
     }
     const float lbx = s.bx, lby = s.by;           // last_frame.ball
 
-    physics_step<RS_KIND_SSL, R>(P, s, d, live);
+    if constexpr (R >= 3) physics_step<RS_KIND_SSL, R>(P, s, d, live, cq, cq + (R + 1) * 32, 32);
+    else physics_step<RS_KIND_SSL, R>(P, s, d, live);
 
-    // ssl_gym_base.py:83-85: the observation is taken BEFORE the reward updates the counter
-    float *o = A.obs + (size_t)e * NOBS;
+    // ssl_gym_base.py:83-85: the observation is taken BEFORE the reward updates the counter.  The row is staged
+    // in the warp's shared-memory tile (over the contact scratch) and leaves with the warp copy of the kernel.
+    __syncwarp(live);
+    float *o = wtile + (threadIdx.x & 31) * NOBS;
     ssl_hw_obs<TASK>(P, s, counter, o);
     float rew = 0.0f; bool dn = false;
     if (DRIB) {                                   // dribbling.py:135-185
@@ -642,10 +654,16 @@ __device__ __forceinline__ void ssl_hw_env_step_match(const DevParams &P, const 
 template <int TASK, int NB, int NY, int BS>
 __global__ void __launch_bounds__(BS)
 k_ssl_hw_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
+    constexpr int R = NB + NY, NOBS = TASK == RS_TASK_SSL_DRIBBLING ? RS_DRIB_OBS : RS_PASS_OBS;
+    constexpr int SCRATCH = R >= 3 ? 2 * (R + 1) * 32 * 4 : 0, WF = 32 * NOBS > SCRATCH ? 32 * NOBS : SCRATCH;
+    __shared__ __align__(128) float smem[BS / 32][WF];
+    float *const wtile = smem[threadIdx.x >> 5];
     const int e = blockIdx.x * BS + threadIdx.x;
+    const int w0 = blockIdx.x * BS + (threadIdx.x & ~31);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
     uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
-    if (e < S.n) ssl_hw_env_step_match<TASK, NB, NY>(P, S, A, e, live);
+    if (e < S.n) ssl_hw_env_step_match<TASK, NB, NY>(P, S, A, e, live, wtile);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, wtile, min(32, S.n - w0), NOBS, tile_flag == nullptr);
     step_end(tile_flag);
 }
 
@@ -865,7 +883,7 @@ k_step(const __grid_constant__ DevParams P, const StatePtrs S, const float *__re
             if (drib) d.drib |= 1u << r;
         }
     }
-    if constexpr (KIND == RS_KIND_VSS && RT >= 1 && RT <= 7) {
+    if constexpr ((KIND == RS_KIND_VSS && RT >= 1 && RT <= 7) || (KIND == RS_KIND_SSL && RT >= 3 && RT <= 7)) {
         // per-lane contact resolve through shared memory (rs_device.cuh): one region per warp
         __shared__ __align__(16) float4 scratch[BS / 32][2 * (RT + 1) * 32];
         float4 *const cq = scratch[threadIdx.x >> 5] + (threadIdx.x & 31);
@@ -1151,11 +1169,18 @@ static StatePtrs state_ptrs(const rs_world *w) {
 //   rs_step SSL 1 v 6 (all seven robots driven)  8.6 vs 24.8 @ 4 096    36.1 vs 57.4 @ 65 536
 // Worlds with more than 7 robots have no register-resident lane-per-match kernel (its
 // generic variant keeps the scene in local memory), so they always go lane per body.
+//
+// RS_OPT_STEP_OVERLAP = 3 (worlds stepped round-robin: consecutive launches overlap freely, the GPU is
+// filled by several launches together) is a throughput regime: issued instructions decide, so every task
+// world with a register-resident kernel runs one lane per match -- us per step, lane per body vs lane per
+// match in rotation: VSS-v0 @ 4 096 2.63 vs 1.69, SSL 1 v 6 @ 4 096 2.40 vs 2.01, SSL 1 v 1 @ 16 384 5.31 vs
+// 2.00 (profiles/r2_overlap.txt).
 static bool use_lane_per_body(const rs_world *w, bool task_kernel) {
     if (w->per_match >= 0) return w->per_match == 0;
     const int R = w->p.n_robots;
     if (R > 7) return true;
     if (R <= 2) return false;
+    if (task_kernel && w->overlap == 3) return false;
     if (w->p.kind == RS_KIND_VSS) return task_kernel ? w->n < 6000 : w->n < 20000;
     return task_kernel ? w->n < 14000 : true;
 }

@@ -300,6 +300,43 @@ __device__ __forceinline__ void vss_walls(const PP &P, const float r, const floa
     if (hy && oy > 0.0f) vy = wall_bounce(P, e, vy);
 }
 
+// SSL robot <-> ball geometry: the robot is the disc of radius rbt_r cut by the chord x_local = dk (the flat
+// kicker mouth; contested_possession.py:224-225 starts the ball 0.1 m ahead of the centre, inside the
+// bounding circle).  (dx, dy) = ball - robot on the phase-start positions, d2 its squared length (already known
+// to be below the bounding-circle contact distance).  Closest point of the shape to the ball centre ->
+// unit normal robot->ball, penetration, contact point offset (world frame).  false: no contact.
+template <class PP>
+__device__ __forceinline__ bool ssl_mouth_contact(const PP &P, const float dx, const float dy, const float d2, const float rth,
+                                                  float &nx, float &ny, float &pen, float &rcx, float &rcy) {
+    float s, c;
+    __sincosf(rth, &s, &c);
+    const float lx = c * dx + s * dy, ly = -s * dx + c * dy;
+    const float bn = sqrtf(d2);
+    float q1x = lx, q1y = ly;
+    if (bn > P.rbt_r) { const float k = P.rbt_r / bn; q1x = lx * k; q1y = ly * k; }
+    float qx, qy;
+    if (q1x <= P.dk) { qx = q1x; qy = q1y; }
+    else { qx = P.dk; qy = clampf(ly, -P.mouth_hc, P.mouth_hc); }
+    const float ex = lx - qx, ey = ly - qy;
+    const float e2 = ex * ex + ey * ey;
+    if (e2 >= P.ball_r * P.ball_r) return false;
+    float lnx, lny;
+    if (e2 > 1e-12f) {
+        const float inv = rsqrtf(e2);
+        lnx = ex * inv; lny = ey * inv; pen = P.ball_r - e2 * inv;
+    } else {
+        const float pr = P.rbt_r - bn, pf = P.dk - lx;
+        if (pf < pr) { lnx = 1.0f; lny = 0.0f; pen = P.ball_r + pf; }
+        else {
+            if (bn > 1e-9f) { lnx = lx / bn; lny = ly / bn; } else { lnx = 1.0f; lny = 0.0f; }
+            pen = P.ball_r + pr;
+        }
+    }
+    nx = c * lnx - s * lny; ny = s * lnx + c * lny;
+    rcx = c * qx - s * qy; rcy = s * qx + c * qy;
+    return true;
+}
+
 // robot <-> ball: detect on (rx, ry, rth) vs (bx, by); impulse on velocities, position
 // corrections accumulated into (cbx, cby) / (crx, cry)
 template <int KIND, class PP>
@@ -317,32 +354,7 @@ __device__ __forceinline__ void ball_robot(const PP &P, float bx, float by, floa
         pen = P.rs_br - d;
         rcx = nx * P.rbt_r; rcy = ny * P.rbt_r;
     } else {
-        float s, c;
-        __sincosf(rth, &s, &c);
-        const float lx = c * dx + s * dy, ly = -s * dx + c * dy;
-        const float bn = sqrtf(d2);
-        float q1x = lx, q1y = ly;
-        if (bn > P.rbt_r) { const float k = P.rbt_r / bn; q1x = lx * k; q1y = ly * k; }
-        float qx, qy;
-        if (q1x <= P.dk) { qx = q1x; qy = q1y; }
-        else { qx = P.dk; qy = clampf(ly, -P.mouth_hc, P.mouth_hc); }
-        const float ex = lx - qx, ey = ly - qy;
-        const float e2 = ex * ex + ey * ey;
-        if (e2 >= P.ball_r * P.ball_r) return;
-        float lnx, lny;
-        if (e2 > 1e-12f) {
-            const float inv = rsqrtf(e2);
-            lnx = ex * inv; lny = ey * inv; pen = P.ball_r - e2 * inv;
-        } else {
-            const float pr = P.rbt_r - bn, pf = P.dk - lx;
-            if (pf < pr) { lnx = 1.0f; lny = 0.0f; pen = P.ball_r + pf; }
-            else {
-                if (bn > 1e-9f) { lnx = lx / bn; lny = ly / bn; } else { lnx = 1.0f; lny = 0.0f; }
-                pen = P.ball_r + pr;
-            }
-        }
-        nx = c * lnx - s * lny; ny = s * lnx + c * lny;
-        rcx = c * qx - s * qy; rcy = s * qx + c * qy;
+        if (!ssl_mouth_contact(P, dx, dy, d2, rth, nx, ny, pen, rcx, rcy)) return;
     }
     const float sx = rvx - rom * rcy, sy = rvy + rom * rcx;   // robot surface velocity at contact
     const float relx = bvx - sx, rely = bvy - sy;
@@ -550,6 +562,80 @@ __device__ __forceinline__ void contacts_via_smem(const PP &P, Scene<RT> &s, uin
     }
 }
 
+// The same for SSL worlds (lane-per-match kernels, R <= 7): the bit of a ball pair only says "inside the
+// bounding circle" -- whether the ball touches the mouth-cut shape is decided here (ssl_mouth_contact, needs
+// the robot's heading, published next to its angular velocity); robot pairs are discs as in VSS.  Run-time
+// constants, scalar forms, same arithmetic and order as ball_robot<SSL> / robot_robot.  Replaces the
+// register-static dispatch (contacts_static) that kept the 1 v 6 task kernel at 231 registers.
+//   q[b] = (x, y, vx, vy) live;  pxy[b] = (x, y) at phase start;  pang[b] = (omega, theta)
+template <int RT, class PP>
+__device__ __forceinline__ void contacts_via_smem_ssl(const PP &P, Scene<RT> &s, uint32_t m, float4 *q, float4 *p0, const int pitch) {
+    static_assert(RT >= 1 && RT <= 7, "3-bit body indices, 21 robot pairs in 63 bits");
+    const int lane = threadIdx.x & 31;
+    float2 *const pxy = reinterpret_cast<float2 *>(p0 - lane) + lane;
+    float2 *const pang = reinterpret_cast<float2 *>(p0 - lane + (RT + 1) * pitch / 2) + lane;
+    q[0] = make_float4(s.bx, s.by, s.bvx, s.bvy); pxy[0] = make_float2(s.bx, s.by);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        q[(r + 1) * pitch] = make_float4(s.x[r], s.y[r], s.vx[r], s.vy[r]);
+        pxy[(r + 1) * pitch] = make_float2(s.x[r], s.y[r]);
+        pang[(r + 1) * pitch] = make_float2(s.om[r], s.th[r]);
+    }
+    constexpr uint64_t TI = rr_table<RT>(false), TJ = rr_table<RT>(true);
+    do {
+        const int p = __ffs((int)m) - 1;
+        m &= m - 1;
+        const bool ball = p < RT;
+        const int k3 = 3 * (p - RT);
+        // normal points F -> S.  ball pairs: F = robot p, S = ball (body 0)
+        const int F = ball ? p + 1 : 1 + (int)((TI >> k3) & 7u), S = ball ? 0 : 1 + (int)((TJ >> k3) & 7u);
+        const float2 pf = pxy[F * pitch], ps = pxy[S * pitch];
+        const float2 af = pang[F * pitch];
+        float4 qf = q[F * pitch], qs = q[S * pitch];
+        const float dx = ps.x - pf.x, dy = ps.y - pf.y;
+        const float d2 = dx * dx + dy * dy;
+        float nx, ny, pen, rcx = 0.0f, rcy = 0.0f;
+        if (ball) {
+            if (!ssl_mouth_contact(P, dx, dy, d2, af.y, nx, ny, pen, rcx, rcy)) continue;
+        } else {
+            float d = 0.0f; nx = 1.0f; ny = 0.0f;
+            if (d2 > 1e-12f) { const float inv = rsqrtf(d2); nx = dx * inv; ny = dy * inv; d = d2 * inv; }
+            pen = P.rs_rr - d;
+        }
+        const float sx = qf.z - af.x * rcy, sy = qf.w + af.x * rcx;      // F's surface velocity at the contact
+        const float relx = qs.z - sx, rely = qs.w - sy;
+        const float vn = relx * nx + rely * ny;
+        if (vn < 0.0f) {
+            if (ball) {
+                const float Jn = -(1.0f + P.e_ball_rbt) * vn * P.inv_wsum;
+                qs.z += Jn * P.wb * nx; qs.w += Jn * P.wb * ny;
+                qf.z -= Jn * P.wr * nx; qf.w -= Jn * P.wr * ny;
+                const float tx = -ny, ty = nx;
+                const float vt = relx * tx + rely * ty;
+                const float Jt = clampf(-vt * P.inv_wsum, -P.mu_ball_rbt * Jn, P.mu_ball_rbt * Jn);
+                qs.z += Jt * P.wb * tx; qs.w += Jt * P.wb * ty;
+                qf.z -= Jt * P.wr * tx; qf.w -= Jt * P.wr * ty;
+            } else {
+                const float Jw = -(1.0f + P.e_rbt_rbt) * vn * 0.5f;       // J * wr with equal masses
+                qf.z -= Jw * nx; qf.w -= Jw * ny; qs.z += Jw * nx; qs.w += Jw * ny;
+            }
+        }
+        const float gS = ball ? P.fb : 0.5f, gF = ball ? P.fr : 0.5f;
+        qs.x += pen * gS * nx; qs.y += pen * gS * ny;
+        qf.x -= pen * gF * nx; qf.y -= pen * gF * ny;
+        q[F * pitch] = qf; q[S * pitch] = qs;
+    } while (m);
+    {
+        const float4 b = q[0];
+        s.bx = b.x; s.by = b.y; s.bvx = b.z; s.bvy = b.w;
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const float4 b = q[(r + 1) * pitch];
+        s.x[r] = b.x; s.y[r] = b.y; s.vx[r] = b.z; s.vy[r] = b.w;
+    }
+}
+
 // register-static resolve: the masks are OR-reduced over the warp (REDUX) and the warp walks
 // the set bits in ascending (= lexicographic) order, jumping to the register-static body of
 // that pair; lanes without that contact fail the body's own distance test.
@@ -726,8 +812,9 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
                 mask = __funnelshift_l(__float_as_uint(fmaf(dx, dx, fmaf(dy, dy, -P.rs_br2))), mask, 1);
             }
             mask |= mrr << R;
-            if (KIND == RS_KIND_VSS && cpitch > 0) {     // constants once inlined
-                if (mask) contacts_via_smem<RT>(P, s, mask, cq, cp0, cpitch);
+            if (cpitch > 0) {                            // constants once inlined
+                if constexpr (KIND == RS_KIND_VSS) { if (mask) contacts_via_smem<RT>(P, s, mask, cq, cp0, cpitch); }
+                else { if (mask) contacts_via_smem_ssl<RT>(P, s, mask, cq, cp0, cpitch); }
             } else {
                 contacts_static<KIND, RT>(P, s, mask, live);
             }
@@ -924,8 +1011,15 @@ __device__ __forceinline__ void tile_acquire(uint32_t *flag, uint32_t *err) {
         int spins = 0;
         for (;;) {
             asm volatile("atom.relaxed.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(flag), "r"(0u), "r"(1u) : "memory");
-            if (old == 0u || ++spins > RS_SPIN_LIMIT) break;
-            __nanosleep(32);
+            if (old == 0u) break;
+            // held by the previous step: poll with plain L2 reads (a thousand warps spinning on atomics would
+            // queue up in front of the very store that frees the tile), then try again
+            uint32_t v;
+            do {
+                __nanosleep(64);
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            } while (v != 0u && ++spins <= RS_SPIN_LIMIT);
+            if (spins > RS_SPIN_LIMIT) break;
         }
         if (old != 0u) atomicAdd(err, 1u);     // timed out: two steps of one world on different streams, or a dead predecessor
     }
