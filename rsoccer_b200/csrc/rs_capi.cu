@@ -405,12 +405,11 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
     if (e < S.n) {
         Scene<R> s;
         load_scene<R>(P, S, e, s);
-        int steps = __ldcg(S.steps + e) & 0xFFFFFF;
-        float info[RS_SSL_INFO];
-#pragma unroll
-        for (int i = 0; i < RS_SSL_INFO; ++i) info[i] = steps == 0 ? 0.0f : __ldcg(S.info + (size_t)i * S.np + e);
-        steps += 1;
         const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
+        const int st = __ldcg(S.steps + e);
+        // reward_shaping_total is never loaded (as in k_vss_env_step): zeroed by a store at the first step of an
+        // episode, updated by fire-and-forget reductions (one RED.ADD.F32 per word = the rounding of load-add-store);
+        // 72 bytes per env-step less, and no second exposed load latency behind the step word
         // ---- _get_commands + convert_actions, static_defenders.py:114-148
         float a[RS_SSL_ACT];
 #pragma unroll
@@ -442,20 +441,31 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         if constexpr (SCR) physics_step<RS_KIND_SSL, R>(P, s, d, live, cq, cq + (R + 1) * 32, 32);
         else physics_step<RS_KIND_SSL, R>(P, s, d, live);
 
+        // ---- the task words (loaded at the top) are first needed here, after the physics
+        int steps = st & 0xFFFFFF;
+        float *const info = S.info + e;                        // word i of this match: info[i * np]
+        const size_t np = (size_t)S.np;
+        if (steps == 0) {
+#pragma unroll
+            for (int i = 0; i < RS_SSL_INFO; ++i) info[i * np] = 0.0f;
+        }
+        steps += 1;
         // ---- _calculate_reward_and_done, static_defenders.py:150-212 / contested_possession.py:136-208
         float rew = 0.0f; bool dn = false;
         if (TASK == RS_TASK_SSL_CONTESTED_POSSESSION) {
+            int cnt = 0;
 #pragma unroll
             for (int r = NB; r < R; ++r)
-                if (fabsf(s.vx[r]) > 0.1f || fabsf(s.vy[r]) > 0.1f) { info[8] += 1.0f; dn = true; }
+                if (fabsf(s.vx[r]) > 0.1f || fabsf(s.vy[r]) > 0.1f) { ++cnt; dn = true; }
+            if (cnt) atomicAdd(info + 8 * np, (float)cnt);
         }
         const float hl = P.half_len, hw = P.half_wid;
-        if (s.x[0] < -0.2f || fabsf(s.y[0]) > hw) { dn = true; info[4] += 1.0f; }
-        else if (s.x[0] > hl - P.pen_len && fabsf(s.y[0]) < P.half_pen_wid) { dn = true; info[1] += 1.0f; }
-        else if (s.bx < 0.0f || fabsf(s.by) > hw) { dn = true; info[2] += 1.0f; }
+        if (s.x[0] < -0.2f || fabsf(s.y[0]) > hw) { dn = true; atomicAdd(info + 4 * np, 1.0f); }
+        else if (s.x[0] > hl - P.pen_len && fabsf(s.y[0]) < P.half_pen_wid) { dn = true; atomicAdd(info + 1 * np, 1.0f); }
+        else if (s.bx < 0.0f || fabsf(s.by) > hw) { dn = true; atomicAdd(info + 2 * np, 1.0f); }
         else if (s.bx > hl) {
             dn = true;
-            if (fabsf(s.by) < P.half_goal_wid) { rew = 5.0f; info[0] += 1.0f; } else { info[3] += 1.0f; }
+            if (fabsf(s.by) < P.half_goal_wid) { rew = 5.0f; atomicAdd(info, 1.0f); } else { atomicAdd(info + 3 * np, 1.0f); }
         } else {
             const float ball_dist_scale = sqrtf(4.0f * hw * hw + hl * hl);
             const float ball_grad_scale = sqrtf(hw * hw + hl * hl) * 0.25f;
@@ -473,13 +483,11 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
 #pragma unroll
             for (int i = 0; i < 4; ++i) en += fabsf((P.J[i][0] * vf + P.J[i][1] * vl + P.J[i][2] * s.om[0]) * P.inv_rw);
             const float er = -en / energy_scale;
-            info[5] += bd; info[6] += bg; info[7] += er;
+            atomicAdd(info + 5 * np, bd); atomicAdd(info + 6 * np, bg); atomicAdd(info + 7 * np, er);
             rew = bd + bg + er;
         }
         const bool tr = steps >= A.max_steps;
         A.reward[e] = rew; A.done[e] = dn ? 1 : 0; A.trunc[e] = tr ? 1 : 0;
-#pragma unroll
-        for (int i = 0; i < RS_SSL_INFO; ++i) S.info[(size_t)i * S.np + e] = info[i];
         if (TASK == RS_TASK_SSL_CONTESTED_POSSESSION) {
             // two draws, no rejection loop: the scalar placement is cheaper than a warp-wide one (7.19 vs 7.34 us)
             if (A.auto_reset && (dn || tr)) {

@@ -257,6 +257,20 @@ __device__ __forceinline__ void walls(const PP &P, float r, float e, float &x, f
     vx = __uint_as_float(__float_as_uint(avx) ^ sgx); vy = __uint_as_float(__float_as_uint(avy) ^ sgy);
 }
 
+// SSL walls, lean form for the lane-per-match kernels.  The two goal-wall boxes start at |x| = x_near = L / 2
+// and the outer x bound lies beyond them, so a body with |x| + r <= x_near can only meet the outer y bound:
+// clamp, and reflect the velocity if it points outward (what walls<SSL>() does there, without mirroring).
+// Anything near a goal line takes the generic routine -- rare: the envs end an episode when the ball or the
+// robot gets there, and un-commanded defenders are placed inside the field.
+template <class PP>
+__device__ __forceinline__ void ssl_walls(const PP &P, const float r, const float e, float &x, float &y, float &vx, float &vy) {
+    if (__builtin_expect(fabsf(x) + r > P.x_near, 0)) { walls<RS_KIND_SSL>(P, r, e, x, y, vx, vy); return; }
+    const float YO = P.y_out - r;
+    const bool hy = fabsf(y) > YO, out = vy * y > 0.0f;
+    y = fmaxf(fminf(y, YO), -YO);
+    if (hy && out) vy = -e * vy;
+}
+
 // VSS walls, lean form for the lane-per-match kernels (7 bodies x 5 sub-steps per step: the
 // largest single block of the sub-step loop).  No mirroring of the velocity, no predicate
 // chains: away from the goal post each axis has ONE limit chosen by the sign of the other
@@ -852,9 +866,9 @@ __device__ __forceinline__ void physics_step(const PP &P, Scene<RT> &s, const Dr
 #pragma unroll
             for (int r = 0; r < R; ++r) vss_walls(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
         } else {
-            walls<KIND>(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
+            ssl_walls(P, P.ball_r, P.e_ball_wall, s.bx, s.by, s.bvx, s.bvy);
 #pragma unroll
-            for (int r = 0; r < R; ++r) walls<KIND>(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
+            for (int r = 0; r < R; ++r) ssl_walls(P, P.rbt_r, P.e_rbt_wall, s.x[r], s.y[r], s.vx[r], s.vy[r]);
         }
 #endif
     }
@@ -989,9 +1003,9 @@ __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.lau
 //                     L2), spinning while a previous step still holds it; then the CTA calls
 //                     griddepcontrol.launch_dependents -- so step k+2 cannot launch before
 //                     every tile of step k has been handed to step k+1;
-//   end of a warp:    __syncwarp, lane 0: __threadfence (cumulative: covers the stores of the
-//                     whole warp), then marks the tile ready.
-// Visibility.  The producer's fence makes its stores visible at L2 before the flag flips.  The
+//   end of a warp:    __syncwarp, lane 0 marks the tile ready with a release store (cumulative:
+//                     covers the stores of the whole warp).
+// Visibility.  The producer's release makes its stores visible at L2 before the flag flips.  The
 // consumer reads the flag with an L2 atomic and everything a predecessor may have written --
 // state, task words, step counter -- with loads that go around L1 (ld.global.cg, issued only after
 // the atomic has returned: the loop exit depends on its value), so no stale line of this SM's
@@ -1027,10 +1041,11 @@ __device__ __forceinline__ void tile_acquire(uint32_t *flag, uint32_t *err) {
 }
 __device__ __forceinline__ void tile_release(uint32_t *flag) {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-        __threadfence();
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(0u) : "memory");
-    }
+    // a release store (MEMBAR.ALL.GPU + ST.STRONG.GPU), cumulative over the warp through the __syncwarp above.
+    // Not __threadfence() + store: that compiles to MEMBAR.SC.GPU ... CCTL.IVALL, a sequentially consistent
+    // fence plus an invalidation of the whole L1 that nothing here needs.
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(0u) : "memory");
 }
 // Start of every task step kernel.  flags: word 0 = error counter, word 1 + i = tile i, where a tile is
 // what one WARP of this kernel works on (32 matches in the lane-per-match kernels, 32 / L matches in
