@@ -205,6 +205,12 @@ int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto
  * the const getters above may run concurrently with each other */
 uint64_t rs_launch_count(const rs_world *w);
 
+/* diagnostics: launches a kernel with the grid, CTA size, parameter block and launch attributes of a
+ * lane-per-match step of this world and NO work (chain == 0: it waits for its predecessor like a serialised
+ * step; != 0: it only triggers its dependents, like an overlapped one) -- the launch floor a step is measured
+ * against (tools/launch_floor.py) */
+int rs_debug_empty_step(rs_world *w, int chain, void *stream);
+
 /* which kernels step this world (diagnostics; the results do not depend on it):
  *   bit 0  task kernels run one lane per BODY (else one lane per MATCH)
  *   bit 1  rs_step runs one lane per BODY

@@ -34,7 +34,7 @@ SYMBOLS = (
     "rs_layout", "rs_field_params", "rs_reset", "rs_step", "rs_get_state", "rs_set_raw",
     "rs_get_raw", "rs_get_t", "rs_set_t", "rs_sync_t", "rs_task_obs_dim", "rs_task_act_dim", "rs_task_reset", "rs_vss_env_step",
     "rs_ssl_env_step", "rs_vss_env_step_host", "rs_ssl_env_step_host", "rs_launch_count", "rs_kernel_flags",
-    "rs_set_option", "rs_get_option",
+    "rs_set_option", "rs_get_option", "rs_debug_empty_step",
 )
 OPT_STEP_OVERLAP, OPT_PDL, OPT_OVERLAP_ERRORS = 1, 2, 3
 
@@ -108,6 +108,7 @@ def lib():
     L.rs_launch_count.argtypes = [vp]
     L.rs_kernel_flags.restype = i32
     L.rs_kernel_flags.argtypes = [vp]
+    L.rs_debug_empty_step.argtypes = [vp, i32, vp]
     L.rs_set_option.argtypes = [vp, i32, i64]
     L.rs_get_option.argtypes = [vp, i32, C.POINTER(i64), vp]
     _lib = L

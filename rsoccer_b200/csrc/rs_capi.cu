@@ -1034,6 +1034,15 @@ __global__ void k_task_reset(const DevParams P, const StatePtrs S, const uint8_t
     }
 }
 
+// launch floor probe (rs_debug_empty_step): the grid, CTA size, parameter block and launch attributes of a step
+// kernel, no work.  chain == 0: waits for its predecessor like a serialised step; else only triggers its dependents.
+__global__ void __launch_bounds__(64)
+k_empty_step(const __grid_constant__ DevParams P, const StatePtrs S, const SslStepArgs A) {
+    if (A.chain == 0) pdl_wait();
+    pdl_release();
+    if (S.n < 0) A.reward[0] = P.dt;          // never true: keeps the parameters alive
+}
+
 // ============================================================================ host side
 
 static thread_local std::string g_err;
@@ -1482,6 +1491,16 @@ int rs_sync_t(rs_world *w, void *stream) {
     return RS_OK;
 }
 uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches.load() : 0; }
+
+int rs_debug_empty_step(rs_world *w, int chain, void *stream) {
+    NEED_STATE(w, "rs_debug_empty_step");
+    SslStepArgs A;
+    memset(&A, 0, sizeof(A));
+    A.chain = chain;
+    launch_step_kernel(w, k_empty_step, (w->n + 63) / 64, 64, (cudaStream_t)stream, w->dp, state_ptrs(w), A);
+    LAUNCH_CHECK("rs_debug_empty_step");
+    return RS_OK;
+}
 
 int rs_kernel_flags(const rs_world *w) {
     if (!w) return 0;
