@@ -500,7 +500,7 @@ template <int RT> constexpr PairTab<RT> make_pair_tab_f0() {
 // In global memory, read through the read-only path (LDG.CONSTANT, L1-resident after the first touch), NOT
 // in __constant__ memory: a user constant bank in the module added 0.1-0.3 us to EVERY kernel
 // launch of the library (7.27 -> 7.57 us for the 4 096-match VSS-v0 step, which never reads the
-// table; gpurun_out/run39.log), far more than the table saves.
+// table; profiles/r1_logs/run39.log), far more than the table saves.
 template <int RT> __device__ const PairTab<RT> g_pair_tab_f0 = make_pair_tab_f0<RT>();
 
 template <int RT, class PP>
