@@ -259,7 +259,8 @@ def run_reference(args, rank, out):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": K, "repeats": reps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["workload"],
+        "config": {"workload": cfg["workload"], "envs_per_gpu": envs, "field_type": 0 if cfg["task"] == "vss" else 2,
+                   "time_step_ms": 25, "substeps": 5,
                    "robosim": "imported" if have_robosim else "absent (rc-robosim 1.2.0 is not installable here)",
                    "note": "rSim timed through the unmodified reference env" if have_robosim else
                            "this arm times the CPU restatement of the same path (oracle/rs_oracle.c, fp64, OpenMP) "

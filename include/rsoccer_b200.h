@@ -118,8 +118,8 @@ int rs_get_state(const rs_world *w, float *d_out, void *stream);
 int rs_set_raw(rs_world *w, const float *d_in, void *stream);
 int rs_get_raw(const rs_world *w, float *d_out, void *stream);
 
-/* World step counter t = Philox counter word 1: 32 bits, wraps modulo 2^32 (rs_set_t rejects
- * larger values).  It is advanced ON THE DEVICE by every task-level step (rs_vss_env_step,
+/* World step counter t = Philox counter word 1: 31 bits, wraps modulo 2^31 (rs_set_t rejects
+ * larger values; bit 31 of its device copies is the tile lock of RS_OPT_STEP_OVERLAP).  It is advanced ON THE DEVICE by every task-level step (rs_vss_env_step,
  * rs_ssl_env_step) -- so a captured CUDA graph replays with fresh noise -- and by nothing else:
  * rs_step draws no random numbers and leaves it alone.  rs_get_t returns the host mirror,
  * exact unless launches were replayed from a graph; rs_sync_t (blocking) reads the device

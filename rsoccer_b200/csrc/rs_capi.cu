@@ -79,11 +79,12 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
-    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
+    const StepTile tile_lock = step_begin<BS>(A.ctr, A.flags, A.chain, w0);
     if (e < S.n) {
         // ---- every global load of the step is issued first: the step counter ahead of the state,
         // so that it is not queued behind 100 KB of requests per SM and Philox can start at once
-        const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
+        // (with step overlap it arrived with the tile lock)
+        const uint32_t t_now = tile_lock.lock ? tile_lock.t : step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
         Scene<R> s;
         load_scene<R>(P, S, e, s);
         const int st = __ldcg(S.steps + e);
@@ -215,7 +216,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
         S.prev[e] = prev;
         __syncwarp(live);      // the rows below overlay the other lanes' contact scratch
         vss_obs<NB, NY, PK>(P, s, wtile + (tid & 31) * NOBS);
-        step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
+        step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now, tile_lock.lock != nullptr);
     }
     // the rows of a warp are one contiguous span of global memory: every lane of the warp (live
     // or not) ships 16-byte pieces of it, coalesced -- half the L2 write sectors of row-per-lane
@@ -228,7 +229,7 @@ k_vss_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Vss
 #pragma unroll
         for (int i = 0; i < NOBS / 4; ++i) { const int k = i * 32 + (tid & 31); if (k < total) dst[k] = src[k]; }
     }
-    step_end(tile_flag);
+    step_end(tile_lock);
 }
 
 
@@ -257,7 +258,7 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     const int p = is_ou ? b - 2 : 0;                           // OU process of this lane (blue 0 is the agent)
     const uint32_t gid = A.env_offset + (uint32_t)ec;
 
-    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
+    const StepTile tile_lock = step_begin<BS>(A.ctr, A.flags, A.chain, w0);
     // ---- loads first: own body, own task word, own action source
     LaneBody s;
     lanes_load<L>(S, R, b, ec, s);
@@ -265,7 +266,7 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     float2 a = make_float2(0.0f, 0.0f);
     if (b == 1) a = __ldcg(A.actions + ec);
     if (is_ou) a = __ldcg(S.ou + (size_t)p * S.np + ec);
-    const uint32_t t_now = step_counter_read<RS_CTR_GROUP * L>(A.ctr, ec);
+    const uint32_t t_now = tile_lock.lock ? tile_lock.t : step_counter_read<RS_CTR_GROUP * L>(A.ctr, ec);
 
     // ---- OU noise under the load latency: normals (2p, 2p + 1) are Box-Muller of the
     // u32 pair (p & 1) of Philox call p / 2 of the (global env id, t, OU) stream
@@ -365,9 +366,9 @@ k_vss_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
             q[0] = nx; q[1] = ny; q[2] = nvx; q[3] = nvy; q[4] = nw;
         }
     }
-    if (valid) step_counter_bump<RS_CTR_GROUP * L>(A.ctr, e, t_now);
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS, tile_flag == nullptr);
-    step_end(tile_flag);
+    if (valid) step_counter_bump<RS_CTR_GROUP * L>(A.ctr, e, t_now, tile_lock.lock != nullptr);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS, tile_lock.lock == nullptr);
+    step_end(tile_lock);
 }
 
 struct SslStepArgs {
@@ -401,11 +402,11 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
     const int w0 = e0 + (tid & ~31);                       // first env of this warp
     const int wrows = min(32, S.n - w0);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
-    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
+    const StepTile tile_lock = step_begin<BS>(A.ctr, A.flags, A.chain, w0);
     if (e < S.n) {
         Scene<R> s;
         load_scene<R>(P, S, e, s);
-        const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
+        const uint32_t t_now = tile_lock.lock ? tile_lock.t : step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
         const int st = __ldcg(S.steps + e);
         // reward_shaping_total is never loaded (as in k_vss_env_step): zeroed by a store at the first step of an
         // episode, updated by fire-and-forget reductions (one RED.ADD.F32 per word = the rounding of load-add-store);
@@ -519,10 +520,10 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
         S.steps[e] = steps;
         __syncwarp(live);          // the rows below overlay the scratch / the placement words an ending lane may still read
         ssl_obs<NB, NY>(P, s, wtile + (tid & 31) * NOBS);
-        step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
+        step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now, tile_lock.lock != nullptr);
     }
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, wtile, wrows, NOBS, tile_flag == nullptr);
-    step_end(tile_flag);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, wtile, wrows, NOBS, tile_lock.lock == nullptr);
+    step_end(tile_lock);
 }
 
 // SSLHWDribblingEnv.step (TASK 3: 1 blue + 4 yellow, dribbling.py) and SSLPassEnduranceEnv.step
@@ -533,7 +534,7 @@ k_ssl_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const Ssl
 // :121), so its `> 15` test never fires and is not restated.
 template <int TASK, int NB, int NY>
 __device__ __forceinline__ void ssl_hw_env_step_match(const DevParams &P, const StatePtrs &S, const SslStepArgs &A,
-                                                      const int e, const unsigned live, float *const wtile) {
+                                                      const int e, const unsigned live, float *const wtile, const StepTile &tile_lock) {
     constexpr int R = NB + NY;
     constexpr bool DRIB = TASK == RS_TASK_SSL_DRIBBLING;
     constexpr int NACT = DRIB ? RS_DRIB_ACT : RS_PASS_ACT, NOBS = DRIB ? RS_DRIB_OBS : RS_PASS_OBS;
@@ -544,7 +545,7 @@ __device__ __forceinline__ void ssl_hw_env_step_match(const DevParams &P, const 
     float counter = steps == 0 ? 0.0f : __ldcg(S.prev + e);
     float info0 = steps == 0 ? 0.0f : __ldcg(S.info + e), info1 = steps == 0 ? 0.0f : __ldcg(S.info + (size_t)S.np + e);
     steps += 1;
-    const uint32_t t_now = step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
+    const uint32_t t_now = tile_lock.lock ? tile_lock.t : step_counter_read<RS_CTR_GROUP>(A.ctr, e, live);
     float a[NACT];
 #pragma unroll
     for (int i = 0; i < NACT; ++i) a[i] = __ldcg(A.actions + (size_t)e * NACT + i);
@@ -657,7 +658,7 @@ __device__ __forceinline__ void ssl_hw_env_step_match(const DevParams &P, const 
     store_scene<R>(P, S, e, s);
     S.steps[e] = steps;
     S.prev[e] = counter;
-    step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now);
+    step_counter_bump<RS_CTR_GROUP>(A.ctr, e, t_now, tile_lock.lock != nullptr);
 }
 template <int TASK, int NB, int NY, int BS>
 __global__ void __launch_bounds__(BS)
@@ -669,10 +670,10 @@ k_ssl_hw_env_step(const __grid_constant__ DevParams P, const StatePtrs S, const 
     const int e = blockIdx.x * BS + threadIdx.x;
     const int w0 = blockIdx.x * BS + (threadIdx.x & ~31);
     const unsigned live = __ballot_sync(0xffffffffu, e < S.n);
-    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
-    if (e < S.n) ssl_hw_env_step_match<TASK, NB, NY>(P, S, A, e, live, wtile);
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, wtile, min(32, S.n - w0), NOBS, tile_flag == nullptr);
-    step_end(tile_flag);
+    const StepTile tile_lock = step_begin<BS>(A.ctr, A.flags, A.chain, w0);
+    if (e < S.n) ssl_hw_env_step_match<TASK, NB, NY>(P, S, A, e, live, wtile, tile_lock);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, wtile, min(32, S.n - w0), NOBS, tile_lock.lock == nullptr);
+    step_end(tile_lock);
 }
 
 
@@ -698,7 +699,7 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     const LaneGroup<L> g;
     const bool is_robot = b >= 1 && b <= R;
 
-    uint32_t *const tile_flag = step_begin<BS>(A.flags, A.chain);
+    const StepTile tile_lock = step_begin<BS>(A.ctr, A.flags, A.chain, w0);
     LaneBody s;
     lanes_load<L>(S, R, b, ec, s);
     uint32_t aux[KW];
@@ -710,7 +711,7 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
     float a[RS_SSL_ACT];
 #pragma unroll
     for (int i = 0; i < RS_SSL_ACT; ++i) a[i] = b == 1 ? __ldcg(A.actions + (size_t)ec * RS_SSL_ACT + i) : 0.0f;
-    const uint32_t t_now = step_counter_read<RS_CTR_GROUP * L>(A.ctr, ec);
+    const uint32_t t_now = tile_lock.lock ? tile_lock.t : step_counter_read<RS_CTR_GROUP * L>(A.ctr, ec);
 
     // ---- _get_commands + convert_actions, static_defenders.py:114-148 (blue 0; the other
     // robots get all-zero rows, rsim.py:129-130)
@@ -817,9 +818,9 @@ k_ssl_env_step_lanes(const __grid_constant__ DevParams P, const StatePtrs S, con
             q[0] = nx; q[1] = ny;
         }
     }
-    if (valid) step_counter_bump<RS_CTR_GROUP * L>(A.ctr, e, t_now);
-    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS, tile_flag == nullptr);
-    step_end(tile_flag);
+    if (valid) step_counter_bump<RS_CTR_GROUP * L>(A.ctr, e, t_now, tile_lock.lock != nullptr);
+    warp_tile_store(A.obs + (size_t)w0 * NOBS, tile + (tid >> 5) * MPW * NOBS, wrows, NOBS, tile_lock.lock == nullptr);
+    step_end(tile_lock);
 }
 
 // simulator.step(cmds), one lane per BODY: any (kind, R <= 31) with L = 2^k >= R + 1
@@ -998,7 +999,7 @@ __global__ void k_task_reset(const DevParams P, const StatePtrs S, const uint8_t
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= S.n) return;
     if (mask && !mask[e]) return;
-    const uint32_t t = ctr[e / RS_CTR_GROUP];
+    const uint32_t t = ctr[e / RS_CTR_GROUP] & RS_T_MASK;
     Scene<0> s;
     task_place<TASK, 0>(P, Rng(seed, env_offset + (uint32_t)e, t, RS_STREAM_RESET), s);
     store_scene<0>(P, S, e, s);
@@ -1077,7 +1078,7 @@ struct rs_world {
     bool host_copy_actions;  // RS_HOST_COPY_ACTIONS=1: stage pinned host actions with a copy instead of reading them in place
     // step-to-step overlap (RS_OPT_STEP_OVERLAP; rs_device.cuh, tile_acquire)
     int overlap;             // 0 off, 1 state through tile flags + grid wait before caller buffers, 2 tile flags only, 3 = 2 + dense CTAs
-    uint32_t *d_flags;       // word 0: error counter; words 1 .. np: tile flags, one per warp of a step kernel (library-owned)
+    uint32_t *d_flags;       // error counter of the step-overlap protocol (library-owned; the tile locks live in d_ctr)
     bool chain_ok;           // the previous launch that touched the state was a flag-protocol step ...
     cudaStream_t chain_stream;   // ... on this stream ...
     int chain_family;        // ... of this kernel family (= tile mapping; a different family starts with a grid-wide wait)
@@ -1329,7 +1330,7 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     w->overlap = 0;
     if (const char *ov = getenv("RS_STEP_OVERLAP")) { const int v = atoi(ov); if (v >= 0 && v <= 3) w->overlap = v; }
     w->n_ctr = w->np / RS_CTR_GROUP;
-    const size_t flag_bytes = ((size_t)w->np + 1) * sizeof(uint32_t);
+    const size_t flag_bytes = 4 * sizeof(uint32_t);
     if (cudaMalloc(&w->d_ctr, w->n_ctr * sizeof(uint32_t)) != cudaSuccess || cudaMemset(w->d_ctr, 0, w->n_ctr * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&w->d_flags, flag_bytes) != cudaSuccess || cudaMemset(w->d_flags, 0, flag_bytes) != cudaSuccess) {
         cudaFree(w->d_ctr); cudaFree(w->d_flags);
@@ -1458,7 +1459,7 @@ int rs_get_raw(const rs_world *w, float *d_out, void *stream) {
 uint64_t rs_get_t(const rs_world *w) { return w ? w->t : 0; }
 int rs_set_t(rs_world *w, uint64_t t) {
     if (!w) return fail(RS_E_INVALID, "rs_set_t: null world");
-    if (t > 0xFFFFFFFFull) return fail(RS_E_INVALID, "rs_set_t: the Philox step counter word has 32 bits");
+    if (t > 0x7FFFFFFFull) return fail(RS_E_INVALID, "rs_set_t: the step counter has 31 bits (bit 31 of its device copies is the tile lock)");
     w->t = t; w->t_dirty = true;
     return RS_OK;
 }
@@ -1487,7 +1488,7 @@ int rs_sync_t(rs_world *w, void *stream) {
     uint32_t t = 0;
     CUDA_TRY(cudaMemcpyAsync(&t, w->d_ctr, sizeof(t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    w->t = t;
+    w->t = t & 0x7FFFFFFFu;
     return RS_OK;
 }
 uint64_t rs_launch_count(const rs_world *w) { return w ? w->launches.load() : 0; }
@@ -1649,7 +1650,7 @@ int rs_vss_env_step(rs_world *w, const float *d_actions, const float *d_normals,
     if (rc) return rc;
     A.seed = w->seed; A.ctr = w->d_ctr; A.env_offset = (uint32_t)w->env_offset;
     launch_vss(w, A, state_ptrs(w), st);
-    w->t = (w->t + 1) & 0xFFFFFFFFull;
+    w->t = (w->t + 1) & 0x7FFFFFFFull;
     LAUNCH_CHECK("rs_vss_env_step");
     return RS_OK;
 }
@@ -1699,7 +1700,7 @@ int rs_ssl_env_step(rs_world *w, int task, const float *d_actions, int auto_rese
         if (w->block == 128) launch_step_kernel(w, k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 128>, g128, 128, st, w->dp, S, A);
         else launch_step_kernel(w, k_ssl_env_step<RS_TASK_SSL_CONTESTED_POSSESSION, 1, 1, 64>, g64, 64, st, w->dp, S, A);
     }
-    w->t = (w->t + 1) & 0xFFFFFFFFull;
+    w->t = (w->t + 1) & 0x7FFFFFFFull;
     LAUNCH_CHECK("rs_ssl_env_step");
     return RS_OK;
 }

@@ -958,6 +958,8 @@ __device__ __forceinline__ void warp_tile_store(float *gdst, const float *stile,
 // and no race: reader and writer of a copy are the same thread.
 //   GL = lanes per counter group = RS_CTR_GROUP x lanes per match (a divisor of 32).
 #define RS_CTR_GROUP 4
+#define RS_T_BUSY 0x80000000u      // bit 31 of a counter copy: a step holds the tile that starts at this copy (step overlap)
+#define RS_T_MASK 0x7fffffffu      // the counter proper: 31 bits
 // The counter words are the only input of the Philox / Box-Muller block, which is meant to
 // run under the latency of the state loads: they are loaded and stored with an L2
 // evict_last policy so that this 64 KB array survives in L2 between two steps of a world
@@ -974,12 +976,13 @@ __device__ __forceinline__ uint32_t step_counter_read(const uint32_t *ctr, const
     if ((lane & (GL - 1)) == 0) {
         asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t) : "l"(ctr + e / RS_CTR_GROUP), "l"(l2_keep_policy()) : "memory");
     }
-    return __shfl_sync(live, t, lane & ~(GL - 1));      // a group's first lane is live whenever any of its lanes is
+    return __shfl_sync(live, t, lane & ~(GL - 1)) & RS_T_MASK;      // a group's first lane is live whenever any of its lanes is
 }
+// skip_lane0: the warp's first copy is the tile lock of the step-overlap protocol and is written by step_end
 template <int GL>
-__device__ __forceinline__ void step_counter_bump(uint32_t *ctr, const int e, const uint32_t t) {
-    if (((threadIdx.x & 31) & (GL - 1)) == 0) {
-        asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(ctr + e / RS_CTR_GROUP), "r"(t + 1u), "l"(l2_keep_policy()) : "memory");
+__device__ __forceinline__ void step_counter_bump(uint32_t *ctr, const int e, const uint32_t t, const bool skip_lane0 = false) {
+    if (((threadIdx.x & 31) & (GL - 1)) == 0 && !(skip_lane0 && (threadIdx.x & 31) == 0)) {
+        asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(ctr + e / RS_CTR_GROUP), "r"((t + 1u) & RS_T_MASK), "l"(l2_keep_policy()) : "memory");
     }
 }
 
@@ -997,75 +1000,79 @@ __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.lau
 // whole grid of step k has finished AND flushed, so launch ramp, state loads and the store
 // drain of consecutive steps are serialised (~7 of 15.5 us at 65 536 matches).  But match i at
 // step k+1 depends only on match i at step k.  With RS_OPT_STEP_OVERLAP the dependency is
-// tracked per 32-match tile (= one warp of the lane-per-match kernels) through one flag word
-// per tile in device memory (library owned, 0 = ready, 1 = a step is working on the tile):
-//   start of a warp:  lane 0 takes the tile with an atomic compare-and-swap 0 -> 1 (performed at
-//                     L2), spinning while a previous step still holds it; then the CTA calls
-//                     griddepcontrol.launch_dependents -- so step k+2 cannot launch before
-//                     every tile of step k has been handed to step k+1;
-//   end of a warp:    __syncwarp, lane 0 marks the tile ready with a release store (cumulative:
-//                     covers the stores of the whole warp).
-// Visibility.  The producer's release makes its stores visible at L2 before the flag flips.  The
-// consumer reads the flag with an L2 atomic and everything a predecessor may have written --
-// state, task words, step counter -- with loads that go around L1 (ld.global.cg, issued only after
-// the atomic has returned: the loop exit depends on its value), so no stale line of this SM's
-// non-coherent L1 can be observed and no L1 invalidation is needed.  (An ld.acquire.gpu here
-// costs a CCTL.IVALL -- the whole L1 -- plus a second L2 round trip before the first state load
-// can issue: 7 % of the warp time at 1 M matches, profiles/r2_overlap.txt.)
+// tracked per TILE = what one warp of a step kernel works on (32 matches in the lane-per-match
+// kernels, 32 / L in the lane-per-body ones).  The tile's lock is bit 31 of the FIRST step-counter
+// copy of its matches (every warp covers whole counter groups), so taking the tile and reading
+// the step counter are one L2 round trip:
+//   start of a warp:  lane 0: old = atomicOr(copy, BUSY).  BUSY clear in old: the tile is ours and
+//                     old is the step counter t.  Else a previous step still holds it: poll with
+//                     plain L2 loads until BUSY clears, retry.  When all warps of the CTA hold their
+//                     tiles the CTA executes griddepcontrol.launch_dependents -- so step k+2 cannot
+//                     launch before every tile of step k has been handed to step k+1;
+//   end of a warp:    the other counter copies get t + 1 as always; __syncwarp; lane 0 writes
+//                     t + 1 (BUSY clear) to the lock copy with a release store (cumulative: covers
+//                     the stores of the whole warp).
+// Visibility.  The producer's release makes its stores visible at L2 before the lock word flips.
+// The consumer reads the lock with an L2 atomic and everything a predecessor may have written --
+// state, task words -- with loads that go around L1 (ld.global.cg, issued only after the atomic
+// has returned: the loop exit depends on its value), so no stale line of this SM's non-coherent L1
+// can be observed and no L1 invalidation is needed.  (ld.acquire.gpu / __threadfence() each
+// compile to a CCTL.IVALL -- the whole L1 -- and a separate flag word costs a second L2 round
+// trip before the first state load can issue: 7 % + 4 % of the warp time at 1 M matches,
+// profiles/r2_overlap.txt.)
 // No deadlock: a programmatic launch starts only after EVERY CTA of the predecessor has
-// executed launch_dependents, i.e. is resident, so a spinning warp always waits for a running
-// one.  The spin is bounded anyway (RS_SPIN_LIMIT polls, then the error word is bumped and the
+// executed launch_dependents, i.e. is resident, so a polling warp always waits for a running
+// one.  The poll is bounded anyway (RS_SPIN_LIMIT polls, then the error word is bumped and the
 // warp goes on): a protocol error must not hang the GPU.
 #ifndef RS_SPIN_LIMIT
 #define RS_SPIN_LIMIT (1 << 19)
 #endif
-__device__ __forceinline__ void tile_acquire(uint32_t *flag, uint32_t *err) {
-    if ((threadIdx.x & 31) == 0) {
-        uint32_t old;
-        int spins = 0;
-        for (;;) {
-            asm volatile("atom.relaxed.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(flag), "r"(0u), "r"(1u) : "memory");
-            if (old == 0u) break;
-            // held by the previous step: poll with plain L2 reads (a thousand warps spinning on atomics would
-            // queue up in front of the very store that frees the tile), then try again
-            uint32_t v;
-            do {
-                __nanosleep(64);
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            } while (v != 0u && ++spins <= RS_SPIN_LIMIT);
-            if (spins > RS_SPIN_LIMIT) break;
-        }
-        if (old != 0u) atomicAdd(err, 1u);     // timed out: two steps of one world on different streams, or a dead predecessor
-    }
-    __syncwarp();
-}
-__device__ __forceinline__ void tile_release(uint32_t *flag) {
-    __syncwarp();
-    // a release store (MEMBAR.ALL.GPU + ST.STRONG.GPU), cumulative over the warp through the __syncwarp above.
-    // Not __threadfence() + store: that compiles to MEMBAR.SC.GPU ... CCTL.IVALL, a sequentially consistent
-    // fence plus an invalidation of the whole L1 that nothing here needs.
-    if ((threadIdx.x & 31) == 0)
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(0u) : "memory");
-}
-// Start of every task step kernel.  flags: word 0 = error counter, word 1 + i = tile i, where a tile is
-// what one WARP of this kernel works on (32 matches in the lane-per-match kernels, 32 / L matches in
-// the lane-per-body kernels) -- the host chains two launches only if they run the same kernel.
+struct StepTile {
+    uint32_t *lock;     // the lock copy of this warp's tile; null: the launch does not take part in the protocol
+    uint32_t t;         // world step counter of this step (valid when lock != null)
+};
+// Start of every task step kernel.  ctr: the step counter copies; err: error counter of the protocol, null =
+// the launch does not take part; w0: first match of this warp.
 //   chain == 0: grid-wide wait first (griddepcontrol.wait), then take the tile (always free)
 //   chain != 0: no grid-wide wait here, the tile is the dependency
-// Returns this warp's tile (null without flags) for step_end.
 template <int BS>
-__device__ __forceinline__ uint32_t *step_begin(uint32_t *flags, const int chain) {
-    uint32_t *tile = nullptr;
+__device__ __forceinline__ StepTile step_begin(uint32_t *ctr, uint32_t *err, const int chain, const int w0) {
+    StepTile T;
+    T.lock = nullptr; T.t = 0u;
     if (chain == 0) pdl_wait();
-    if (flags) {
-        tile = flags + 1 + ((blockIdx.x * BS + threadIdx.x) >> 5);
-        tile_acquire(tile, flags);
+    if (err) {
+        T.lock = ctr + w0 / RS_CTR_GROUP;
+        uint32_t old = 0u;
+        if ((threadIdx.x & 31) == 0) {
+            int spins = 0;
+            for (;;) {
+                asm volatile("atom.relaxed.gpu.global.or.b32 %0, [%1], %2;" : "=r"(old) : "l"(T.lock), "r"(RS_T_BUSY) : "memory");
+                if (!(old & RS_T_BUSY)) break;
+                // held by the previous step: poll with plain L2 reads (a thousand warps spinning on atomics
+                // would queue up in front of the very store that frees the tile), then try again
+                uint32_t v;
+                do {
+                    __nanosleep(64);
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(T.lock) : "memory");
+                } while ((v & RS_T_BUSY) && ++spins <= RS_SPIN_LIMIT);
+                if (spins > RS_SPIN_LIMIT) { atomicAdd(err, 1u); old = v; break; }   // timed out: a dead predecessor, or one world on two streams
+            }
+        }
+        T.t = __shfl_sync(0xffffffffu, old, 0) & RS_T_MASK;
         // the CTA's trigger must not fire before ALL its warps hold their tiles (a CTA counts as triggered
         // once any of its threads has executed launch_dependents): otherwise step k+2 could start and
         // wait for a tile that step k+1 has not taken yet
         if (BS > 32) __syncthreads();
     }
     pdl_release();
-    return tile;
+    return T;
 }
-__device__ __forceinline__ void step_end(uint32_t *tile) { if (tile) tile_release(tile); }
+// End of the kernel, after the warp's last global store.  A release store (MEMBAR.ALL.GPU + ST.STRONG.GPU),
+// cumulative over the warp through the __syncwarp.  Not __threadfence() + store: that compiles to MEMBAR.SC.GPU
+// ... CCTL.IVALL, a sequentially consistent fence plus an invalidation of the whole L1 that nothing here needs.
+__device__ __forceinline__ void step_end(const StepTile &T) {
+    if (!T.lock) return;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(T.lock), "r"((T.t + 1u) & RS_T_MASK) : "memory");
+}

@@ -210,9 +210,9 @@ __device__ __forceinline__ void lanes_physics_step(const PP &P, const int R, con
             }
             __syncwarp();
         }
-        // (f) walls (VSS: the lean form of the lane-per-match kernels, same decisions and arithmetic)
+        // (f) walls (the lean forms of the lane-per-match kernels, same decisions and arithmetic)
         if constexpr (KIND == RS_KIND_VSS) vss_walls(P, rad, ew, s.x, s.y, s.vx, s.vy);
-        else walls<KIND>(P, rad, ew, s.x, s.y, s.vx, s.vy);
+        else ssl_walls(P, rad, ew, s.x, s.y, s.vx, s.vy);
     }
 }
 
