@@ -262,20 +262,9 @@ __device__ __forceinline__ void walls(const PP &P, float r, float e, float &x, f
 // clamp, and reflect the velocity if it points outward (what walls<SSL>() does there, without mirroring).
 // Anything near a goal line takes the generic routine -- rare: the envs end an episode when the ball or the
 // robot gets there, and un-commanded defenders are placed inside the field.
-// The generic routine as ONE out-of-line copy: inlined per body it put 8 x 130 instructions of never-taken code into the
-// sub-step loop of the 1 v 6 kernel (28 KB per iteration: `no_instruction` 0.60 stalls per issued instruction).
-// (By value in, by value out: references would force the caller's scene registers into local memory.)
-__device__ __noinline__ float4 ssl_walls_near_goal(const DevParams &P, const float r, const float e, float4 b) {
-    walls<RS_KIND_SSL>(P, r, e, b.x, b.y, b.z, b.w);
-    return b;
-}
 template <class PP>
 __device__ __forceinline__ void ssl_walls(const PP &P, const float r, const float e, float &x, float &y, float &vx, float &vy) {
-    if (__builtin_expect(fabsf(x) + r > P.x_near, 0)) {
-        const float4 b = ssl_walls_near_goal(P, r, e, make_float4(x, y, vx, vy));
-        x = b.x; y = b.y; vx = b.z; vy = b.w;
-        return;
-    }
+    if (__builtin_expect(fabsf(x) + r > P.x_near, 0)) { walls<RS_KIND_SSL>(P, r, e, x, y, vx, vy); return; }
     const float YO = P.y_out - r;
     const bool hy = fabsf(y) > YO, out = vy * y > 0.0f;
     y = fmaxf(fminf(y, YO), -YO);
