@@ -334,19 +334,10 @@ class Workload:
         self.G = K * self.M // math.gcd(K, self.M)
         self.worlds, self.acts, self.outs = [], [], []
         gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+        self.seed_base, self.rank = seed_base, rank
         for m in range(self.M):
-            off = ((seed_base * 64 + rank) * self.M + m) * envs
-            if self.task == "vss":
-                w = E.BatchedWorld(E.KIND_VSS, 0, 3, 3, 25, envs, device=dev, seed=2024, env_offset=off)
-                self.tid, ad = E.TASK_VSS_V0, 2
-            elif self.task == "sd":
-                w = E.BatchedWorld(E.KIND_SSL, 2, 1, 6, 25, envs, device=dev, seed=2024, env_offset=off)
-                self.tid, ad = E.TASK_SSL_STATIC_DEFENDERS_V0, 5
-            else:
-                w = E.BatchedWorld(E.KIND_SSL, 2, 1, 1, 25, envs, device=dev, seed=2024, env_offset=off)
-                self.tid, ad = E.TASK_SSL_CONTESTED_POSSESSION_V0, 5
+            w, ad = self.new_world(envs, ((seed_base * 64 + rank) * self.M + m) * envs)
             w.set_option(_lib.OPT_STEP_OVERLAP, overlap)
-            w.task_reset(self.tid)
             self.worlds.append(w)
             self.acts.append((torch.rand(envs, ad, generator=gen) * 2 - 1).to(dev))
             self.outs.append(w.alloc_outputs(self.tid))
@@ -361,6 +352,20 @@ class Workload:
             nbny = "1,6" if self.task == "sd" else "1,1"
             self.kernel = ("k_ssl_env_step_lanes<%s> (one lane per body)" % nbny if flags & 1 else
                            "k_ssl_env_step<%s,64> (one lane per match)" % nbny)
+
+    def new_world(self, envs, env_offset):
+        E, dev = self.E, self.dev
+        if self.task == "vss":
+            w = E.BatchedWorld(E.KIND_VSS, 0, 3, 3, 25, envs, device=dev, seed=2024, env_offset=env_offset)
+            self.tid, ad = E.TASK_VSS_V0, 2
+        elif self.task == "sd":
+            w = E.BatchedWorld(E.KIND_SSL, 2, 1, 6, 25, envs, device=dev, seed=2024, env_offset=env_offset)
+            self.tid, ad = E.TASK_SSL_STATIC_DEFENDERS_V0, 5
+        else:
+            w = E.BatchedWorld(E.KIND_SSL, 2, 1, 1, 25, envs, device=dev, seed=2024, env_offset=env_offset)
+            self.tid, ad = E.TASK_SSL_CONTESTED_POSSESSION_V0, 5
+        w.task_reset(self.tid)
+        return w, ad
 
     def step(self, i):
         m = i % self.M
@@ -396,7 +401,7 @@ class Workload:
         self.worlds = []
 
 
-def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_steps=50, clock_index=None):
+def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_steps=50, clock_index=None, pipelined=False):
     """settle -> capture -> W warm-up launches -> timed graph replays; then the e2e loop."""
     res = {}
     with torch.cuda.stream(stream):
@@ -489,18 +494,76 @@ def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_
             t = torch.tensor([ms_e, ms_c], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e, ms_c = float(t[0].item()), float(t[1].item())
+        # the same through the split-phase calls: TWO env groups of N / 2 matches on two streams, group A steps while
+        # group B's outputs cross PCIe (each group: wait for its outputs, start its next step, as a consumer that
+        # works on one group at a time would).  Every step still moves its actions in and its outputs out.
+        pipe = None
+        if pipelined and N % 2 == 0:
+            n2 = N // 2
+            base = ((wl.seed_base * 64 + wl.rank + 32) * 64) * N
+            groups, gbufs, gst = [], [], [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+            for k in range(2):
+                wk, _ = wl.new_world(n2, base + k * n2)
+                ha = torch.empty(n2, wl.act_dim, dtype=torch.float32).pin_memory()
+                ha.copy_(wl.acts[0][k * n2:(k + 1) * n2].cpu())
+                groups.append(wk)
+                gbufs.append((ha,) + tuple(wk.alloc_host_outputs(wl.tid)))
+                da = wl.acts[0][k * n2:(k + 1) * n2].contiguous()
+                for _ in range(wl.cfg["settle"]):             # the contact density of the timed worlds
+                    if wl.task == "vss":
+                        wk.vss_env_step(da, max_steps=wl.cfg["max_steps"])
+                    else:
+                        wk.ssl_env_step(wl.tid, da, max_steps=wl.cfg["max_steps"])
+            torch.cuda.synchronize()
+
+            def begin(k):
+                with torch.cuda.stream(gst[k]):
+                    if wl.task == "vss":
+                        groups[k].vss_env_step_host_begin(*gbufs[k], max_steps=wl.cfg["max_steps"])
+                    else:
+                        groups[k].ssl_env_step_host_begin(wl.tid, *gbufs[k], max_steps=wl.cfg["max_steps"])
+
+            def run(steps):
+                begin(0); begin(1)
+                for _ in range(steps - 1):
+                    groups[0].host_step_wait(); begin(0)
+                    groups[1].host_step_wait(); begin(1)
+                groups[0].host_step_wait(); groups[1].host_step_wait()
+
+            run(3)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run(e2e_steps)
+            torch.cuda.synchronize()
+            ms_p = (time.perf_counter() - t0) * 1e3
+            if world > 1:
+                t = torch.tensor([ms_p], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_p = float(t.item())
+            for wk in groups:
+                wk.close()
+            pipe = {"value": N * world * e2e_steps / (ms_p * 1e-3), "unit": UNIT, "steps": e2e_steps,
+                    "ms_per_step": ms_p / e2e_steps, "frac_of_ceiling": ms_c / ms_p,
+                    "what": "two env groups of %d matches on two streams through rs_*_env_step_host_begin / "
+                            "rs_host_step_wait: one group steps while the other's outputs cross PCIe; host wall "
+                            "clock around the loop (two streams), same bytes per step as the blocking call" % n2}
         h2d = N * wl.act_dim * 4
         res["e2e"] = {
             "value": N * world * e2e_steps / (ms_e * 1e-3), "unit": UNIT, "steps": e2e_steps,
             "ms_per_step": ms_e / e2e_steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "api": ("rs_vss_env_step_host" if wl.task == "vss" else "rs_ssl_env_step_host") +
-                   " (pinned host buffers: actions read over PCIe by the kernel, one packed D2H of obs/reward/done/trunc, sync)",
+            "api": ("rs_vss_env_step_host (pinned host buffers: actions read over PCIe by the kernel" if wl.task == "vss" else
+                    "rs_ssl_env_step_host (pinned host buffers: actions staged with one H2D copy") +
+                   ", one packed D2H of obs/reward/done/trunc, sync)",
             "pcie_gbs": (h2d + d2h) / (ms_e * 1e-3 / e2e_steps) / 1e9,
             "d2h_ceiling_gbs": d2h / (ms_c * 1e-3 / e2e_steps) / 1e9,
             "d2h_ceiling_what": "plain cudaMemcpyAsync of the same %d-byte block + sync, %d rank(s) at once: the box's own "
                                 "limit for this transfer" % (d2h, world),
             "frac_of_ceiling": (ms_c / ms_e),
         }
+        if pipe:
+            res["e2e"]["pipelined"] = pipe
     del graph
     return res
 
@@ -614,7 +677,7 @@ def main():
     wl = Workload(torch, E, args.config, cfg, envs, dev, rank, args.overlap, K)
     launches0 = sum(w.launches for w in wl.worlds)
     res = measure(torch, dist, wl, K, W, args.min_ms, stream, world, dev, e2e_steps=max(10, args.e2e_steps),
-                  clock_index=local_rank)
+                  clock_index=local_rank, pipelined=True)
     main_sum = summarise(wl, res, K, W, world, peak, peak_src)
     launches_timed = res["steps_timed"]
     extras = {}

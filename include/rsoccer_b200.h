@@ -149,10 +149,15 @@ int rs_sync_t(rs_world *w, void *stream);
  * sets the option again afterwards: the next step then starts with a grid-wide wait.
  * RS_OPT_PDL (default 1): launch step kernels with programmatic stream serialization.
  * RS_OPT_OVERLAP_ERRORS (read only, blocking): tiles whose wait timed out -- always 0 unless
- * one world was stepped from two streams at once. */
+ * one world was stepped from two streams at once.
+ * RS_OPT_HOST_COPY_ACTIONS (default -1; RS_HOST_COPY_ACTIONS in the environment): how the *_host steps
+ * fetch PINNED host actions.  0: the step kernel reads them in place over PCIe (no H2D copy).  1: staged
+ * with a copy.  -1: in place only when a match's action row is 8 bytes (VSS-v0: coalesced), else the copy
+ * (the 20-byte rows of the SSL tasks would cross the link five times).  Pageable memory is always copied. */
 #define RS_OPT_STEP_OVERLAP 1
 #define RS_OPT_PDL 2
 #define RS_OPT_OVERLAP_ERRORS 3
+#define RS_OPT_HOST_COPY_ACTIONS 4
 int rs_set_option(rs_world *w, int option, int64_t value);
 int rs_get_option(const rs_world *w, int option, int64_t *value, void *stream);
 
@@ -200,6 +205,21 @@ int rs_vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset, in
 int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto_reset,
                          int max_steps, float *h_obs, float *h_reward, uint8_t *h_done,
                          uint8_t *h_trunc, void *stream);
+
+/* Split-phase host steps (the step_async / step_wait pair of gymnasium's VectorEnv): *_begin enqueues the actions'
+ * fetch, the fused step and the D2H copies on `stream` and returns at once; rs_host_step_wait blocks until the
+ * outputs of that step have landed in the host buffers (no-op when nothing is pending).  One step may be pending
+ * per world (a second *_begin / *_host returns RS_E_STATE); h_actions and the output buffers belong to the library
+ * until the wait returns.  What it is for: double-buffered env groups -- two worlds on two streams, one computes
+ * while the other's observations cross PCIe, the consumer works on one group while the other steps (bench.py
+ * `e2e.pipelined`) -- or overlapping the transfer with the caller's own host work. */
+int rs_vss_env_step_host_begin(rs_world *w, const float *h_actions, int auto_reset, int max_steps,
+                               float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc,
+                               void *stream);
+int rs_ssl_env_step_host_begin(rs_world *w, int task, const float *h_actions, int auto_reset,
+                               int max_steps, float *h_obs, float *h_reward, uint8_t *h_done,
+                               uint8_t *h_trunc, void *stream);
+int rs_host_step_wait(rs_world *w);
 
 /* number of kernels this handle has launched so far (bench.py gpu_launches); atomic, so
  * the const getters above may run concurrently with each other */

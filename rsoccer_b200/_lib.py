@@ -35,8 +35,9 @@ SYMBOLS = (
     "rs_get_raw", "rs_get_t", "rs_set_t", "rs_sync_t", "rs_task_obs_dim", "rs_task_act_dim", "rs_task_reset", "rs_vss_env_step",
     "rs_ssl_env_step", "rs_vss_env_step_host", "rs_ssl_env_step_host", "rs_launch_count", "rs_kernel_flags",
     "rs_set_option", "rs_get_option", "rs_debug_empty_step",
+    "rs_vss_env_step_host_begin", "rs_ssl_env_step_host_begin", "rs_host_step_wait",
 )
-OPT_STEP_OVERLAP, OPT_PDL, OPT_OVERLAP_ERRORS = 1, 2, 3
+OPT_STEP_OVERLAP, OPT_PDL, OPT_OVERLAP_ERRORS, OPT_HOST_COPY_ACTIONS = 1, 2, 3, 4
 
 
 class RsError(RuntimeError):
@@ -102,6 +103,9 @@ def lib():
     L.rs_ssl_env_step.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.rs_vss_env_step_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.rs_ssl_env_step_host.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.rs_vss_env_step_host_begin.argtypes = L.rs_vss_env_step_host.argtypes
+    L.rs_ssl_env_step_host_begin.argtypes = L.rs_ssl_env_step_host.argtypes
+    L.rs_host_step_wait.argtypes = [vp]
     L.rs_task_act_dim.restype = i32
     L.rs_task_act_dim.argtypes = [i32]
     L.rs_launch_count.restype = u64

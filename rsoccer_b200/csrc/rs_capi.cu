@@ -1075,7 +1075,7 @@ struct rs_world {
     int lane_block;          // CTA size of the lane-per-body kernels
     int packed;              // 1: packed fp32x2 instruction forms in the VssF0 kernels; 0: scalar forms; -1: by world size
     bool pdl;                // step kernels are launched with programmatic stream serialization (RS_PDL=0 turns it off)
-    bool host_copy_actions;  // RS_HOST_COPY_ACTIONS=1: stage pinned host actions with a copy instead of reading them in place
+    int host_copy_actions;   // RS_OPT_HOST_COPY_ACTIONS: 1 stage pinned host actions with a copy, 0 the kernel reads them in place, -1 by row size
     // step-to-step overlap (RS_OPT_STEP_OVERLAP; rs_device.cuh, tile_acquire)
     int overlap;             // 0 off, 1 state through tile flags + grid wait before caller buffers, 2 tile flags only, 3 = 2 + dense CTAs
     uint32_t *d_flags;       // error counter of the step-overlap protocol (library-owned; the tile locks live in d_ctr)
@@ -1088,6 +1088,8 @@ struct rs_world {
     int s_act_dim, s_obs_dim;
     const void *h_act_seen;  // last host action pointer looked up with cudaPointerGetAttributes ...
     const float *h_act_dev;  // ... and its device alias (null: pageable, staged with a copy)
+    cudaEvent_t host_done;   // split-phase host step: recorded behind the D2H copies of rs_*_env_step_host_begin
+    bool host_pending;       // ... and not waited for yet
 };
 
 // Every entry point that launches or allocates runs on the world's own device, whatever device is
@@ -1321,8 +1323,8 @@ int rs_create(int kind, int field_type, int n_blue, int n_yellow, int time_step_
     if (const char *ls = getenv("RS_PACKED")) w->packed = atoi(ls) != 0;
     w->pdl = true;
     if (const char *ls = getenv("RS_PDL")) w->pdl = atoi(ls) != 0;
-    w->host_copy_actions = false;
-    if (const char *ls = getenv("RS_HOST_COPY_ACTIONS")) w->host_copy_actions = atoi(ls) != 0;
+    w->host_copy_actions = -1;
+    if (const char *ls = getenv("RS_HOST_COPY_ACTIONS")) w->host_copy_actions = atoi(ls) != 0 ? 1 : 0;
     if (const char *bs = getenv("RS_LANE_BLOCK")) { const int b = atoi(bs); if (b == 64 || b == 128 || b == 256) w->lane_block = b; }
     w->f0 = matches_vss_f0(w->dp) ? 1 : 0;
     if (const char *nv = getenv("RS_NO_PRESET")) { if (atoi(nv) == 1) w->f0 = 0; }
@@ -1347,6 +1349,7 @@ int rs_destroy(rs_world *w) {
     {
         DeviceGuard dg(w->device);
         cudaFree(w->s_actions); cudaFree(w->s_obs);      // s_reward / s_done / s_trunc live inside s_obs's allocation
+        if (w->host_done) cudaEventDestroy(w->host_done);
         cudaFree(w->d_ctr); cudaFree(w->d_flags);
     }
     delete w;
@@ -1519,6 +1522,10 @@ int rs_set_option(rs_world *w, int option, int64_t value) {
         case RS_OPT_PDL:
             w->pdl = value != 0; w->chain_ok = false;
             return RS_OK;
+        case RS_OPT_HOST_COPY_ACTIONS:
+            if (value < -1 || value > 1) return fail(RS_E_INVALID, "rs_set_option: RS_OPT_HOST_COPY_ACTIONS takes -1, 0 or 1");
+            w->host_copy_actions = (int)value; w->h_act_seen = nullptr;
+            return RS_OK;
         default:
             return fail(RS_E_INVALID, "rs_set_option: unknown or read-only option");
     }
@@ -1528,6 +1535,7 @@ int rs_get_option(const rs_world *w, int option, int64_t *value, void *stream) {
     switch (option) {
         case RS_OPT_STEP_OVERLAP: *value = w->overlap; return RS_OK;
         case RS_OPT_PDL: *value = w->pdl ? 1 : 0; return RS_OK;
+        case RS_OPT_HOST_COPY_ACTIONS: *value = w->host_copy_actions; return RS_OK;
         case RS_OPT_OVERLAP_ERRORS: {
             ON_DEVICE(w, "rs_get_option");
             uint32_t e = 0;
@@ -1724,15 +1732,21 @@ static int ensure_scratch(rs_world *w, int act_dim, int obs_dim) {
 }
 
 // The actions of a host-buffer step as the kernel will read them.  Pinned host memory is mapped
-// into the device address space (UVA): the kernel loads the 8-20 bytes per match straight over
-// PCIe while its state loads are in flight, which saves the separate H2D copy and its latency
-// (248 -> 239 us per 65 536-match VSS-v0 step).  Pageable memory is staged with a copy as before.
+// into the device address space (UVA), so a kernel can load the actions straight over PCIe while its
+// state loads are in flight, which saves the separate H2D copy and its latency -- IF the rows are read
+// coalesced.  VSS-v0 (one float2 per match, 256 contiguous bytes per warp): 248 -> 237 us per 65 536-match
+// step, 44.6 -> 42.7 us at 4 096.  The SSL tasks read five scalars at a 20-byte stride, i.e. every line
+// crosses the link five times: in place 54.9 / 79.9 / 282 us against 41.6 / 59.3 / 190 us with the copy
+// (SSLStaticDefenders-v0 at 4 096, SSLContestedPossession-v0 at 16 384, SSLStaticDefenders-v0 at 65 536;
+// profiles/r2_e2e_probe.txt).  So by default (-1) only 8-byte rows are read in place; RS_OPT_HOST_COPY_ACTIONS
+// forces either.  Pageable memory is always staged with a copy.
 // The pointer lookup is cached per handle: a rollout loop passes the same buffer every step.
 static const float *host_actions_on_device(rs_world *w, const float *h_actions, size_t bytes, cudaStream_t st) {
+    const bool copy = w->host_copy_actions >= 0 ? w->host_copy_actions != 0 : bytes != 8u * (size_t)w->n;
     if (h_actions != w->h_act_seen) {
         cudaPointerAttributes at;
         w->h_act_seen = h_actions; w->h_act_dev = nullptr;
-        if (!w->host_copy_actions && cudaPointerGetAttributes(&at, h_actions) == cudaSuccess &&
+        if (!copy && cudaPointerGetAttributes(&at, h_actions) == cudaSuccess &&
             at.type == cudaMemoryTypeHost && at.devicePointer)
             w->h_act_dev = static_cast<const float *>(at.devicePointer);
         cudaGetLastError();
@@ -1745,7 +1759,8 @@ static const float *host_actions_on_device(rs_world *w, const float *h_actions, 
     return w->s_actions;
 }
 
-static int host_epilogue(rs_world *w, int obs_dim, float *h_obs, float *h_reward, uint8_t *h_done,
+// D2H of the four outputs: one copy when the caller's buffers are the packed block, else four
+static int host_copy_out(rs_world *w, int obs_dim, float *h_obs, float *h_reward, uint8_t *h_done,
                          uint8_t *h_trunc, cudaStream_t st) {
     const size_t n = (size_t)w->n, ob = sizeof(float) * n * obs_dim;
     if (reinterpret_cast<char *>(h_reward) == reinterpret_cast<char *>(h_obs) + ob &&
@@ -1757,7 +1772,19 @@ static int host_epilogue(rs_world *w, int obs_dim, float *h_obs, float *h_reward
         CUDA_TRY(cudaMemcpyAsync(h_done, w->s_done, n, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(h_trunc, w->s_trunc, n, cudaMemcpyDeviceToHost, st));
     }
-    CUDA_TRY(cudaStreamSynchronize(st));
+    return RS_OK;
+}
+// blocking form: the call returns when the outputs have landed.  split-phase form (begin = true): an event is
+// recorded behind the copies and rs_host_step_wait blocks on it -- the caller overlaps this world's transfer with
+// the step of ANOTHER world (double-buffered env groups) or with its own host work.
+static int host_epilogue(rs_world *w, int obs_dim, float *h_obs, float *h_reward, uint8_t *h_done,
+                         uint8_t *h_trunc, cudaStream_t st, bool begin) {
+    const int rc = host_copy_out(w, obs_dim, h_obs, h_reward, h_done, h_trunc, st);
+    if (rc) return rc;
+    if (!begin) { CUDA_TRY(cudaStreamSynchronize(st)); return RS_OK; }
+    if (!w->host_done) CUDA_TRY(cudaEventCreateWithFlags(&w->host_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(w->host_done, st));
+    w->host_pending = true;
     return RS_OK;
 }
 
@@ -1768,10 +1795,16 @@ static int host_epilogue(rs_world *w, int obs_dim, float *h_obs, float *h_reward
 // against four smaller copies on a second stream (284 us: the smaller copies lose more than
 // the 17 us kernel hides), the kernel storing straight into the mapped host buffers (267 us), and (round 1g)
 // the packed copy as two halves on two streams / copy engines (239 vs 234 us: one link, one more launch).
-int rs_vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset, int max_steps,
-                         float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc,
-                         void *stream) {
+// Round 2 re-measured the pipelined form with UNEQUAL sub-ranges (1/4 + 3/4, 1/8 + 3/8 + 1/2: a small first launch
+// so that the link starts early, early chunks copied on a second stream behind events): 240 / 244 us against 237 us
+// -- each cross-stream event edge costs the few microseconds the earlier start gains -- and 54 vs 43 us at 4 096
+// matches (profiles/r2_e2e_probe.txt).  The call runs at 0.86 of the plain copy of its outputs; what is left is one
+// launch from idle, a 13 us kernel and the copy's start-up.
+static int vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset, int max_steps,
+                             float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc,
+                             void *stream, bool begin) {
     NEED_STATE(w, "rs_vss_env_step_host");
+    if (w->host_pending) return fail(RS_E_STATE, "rs_vss_env_step_host: a split-phase host step of this world is pending (rs_host_step_wait first)");
     if (!h_actions || !h_obs || !h_reward || !h_done || !h_trunc)
         return fail(RS_E_INVALID, "rs_vss_env_step_host: null argument");
     const int od = rs_task_obs_dim(w, RS_TASK_VSS_V0);
@@ -1780,15 +1813,30 @@ int rs_vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset, in
     cudaStream_t st = (cudaStream_t)stream;
     const float *d_act = host_actions_on_device(w, h_actions, sizeof(float) * (size_t)w->n * RS_VSS_ACT, st);
     if (!d_act) return RS_E_CUDA;
+    // a host step ends with a synchronize: its launch starts on an idle GPU and gains nothing from the tile protocol,
+    // so it is launched as if RS_OPT_STEP_OVERLAP were 0 (mode 3 would pick the dense build, which packs the grid onto
+    // 93 of the 148 SMs, and the lane-per-match kernels for small worlds)
+    const int ov = w->overlap;
+    w->overlap = 0;
     rc = rs_vss_env_step(w, d_act, nullptr, auto_reset, max_steps, w->s_obs, w->s_reward, w->s_done, w->s_trunc, nullptr, stream);
+    w->overlap = ov;
     if (rc) return rc;
-    return host_epilogue(w, od, h_obs, h_reward, h_done, h_trunc, st);
+    return host_epilogue(w, od, h_obs, h_reward, h_done, h_trunc, st, begin);
+}
+int rs_vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset, int max_steps,
+                         float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc, void *stream) {
+    return vss_env_step_host(w, h_actions, auto_reset, max_steps, h_obs, h_reward, h_done, h_trunc, stream, false);
+}
+int rs_vss_env_step_host_begin(rs_world *w, const float *h_actions, int auto_reset, int max_steps,
+                               float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc, void *stream) {
+    return vss_env_step_host(w, h_actions, auto_reset, max_steps, h_obs, h_reward, h_done, h_trunc, stream, true);
 }
 
-int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto_reset,
-                         int max_steps, float *h_obs, float *h_reward, uint8_t *h_done,
-                         uint8_t *h_trunc, void *stream) {
+static int ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto_reset,
+                             int max_steps, float *h_obs, float *h_reward, uint8_t *h_done,
+                             uint8_t *h_trunc, void *stream, bool begin) {
     NEED_STATE(w, "rs_ssl_env_step_host");
+    if (w->host_pending) return fail(RS_E_STATE, "rs_ssl_env_step_host: a split-phase host step of this world is pending (rs_host_step_wait first)");
     if (!h_actions || !h_obs || !h_reward || !h_done || !h_trunc)
         return fail(RS_E_INVALID, "rs_ssl_env_step_host: null argument");
     const int od = rs_task_obs_dim(w, task);
@@ -1800,9 +1848,28 @@ int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto
     cudaStream_t st = (cudaStream_t)stream;
     const float *d_act = host_actions_on_device(w, h_actions, sizeof(float) * (size_t)w->n * ad, st);
     if (!d_act) return RS_E_CUDA;
+    const int ov = w->overlap;            // as in rs_vss_env_step_host
+    w->overlap = 0;
     rc = rs_ssl_env_step(w, task, d_act, auto_reset, max_steps, w->s_obs, w->s_reward, w->s_done, w->s_trunc, nullptr, stream);
+    w->overlap = ov;
     if (rc) return rc;
-    return host_epilogue(w, od, h_obs, h_reward, h_done, h_trunc, st);
+    return host_epilogue(w, od, h_obs, h_reward, h_done, h_trunc, st, begin);
+}
+int rs_ssl_env_step_host(rs_world *w, int task, const float *h_actions, int auto_reset, int max_steps,
+                         float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc, void *stream) {
+    return ssl_env_step_host(w, task, h_actions, auto_reset, max_steps, h_obs, h_reward, h_done, h_trunc, stream, false);
+}
+int rs_ssl_env_step_host_begin(rs_world *w, int task, const float *h_actions, int auto_reset, int max_steps,
+                               float *h_obs, float *h_reward, uint8_t *h_done, uint8_t *h_trunc, void *stream) {
+    return ssl_env_step_host(w, task, h_actions, auto_reset, max_steps, h_obs, h_reward, h_done, h_trunc, stream, true);
+}
+int rs_host_step_wait(rs_world *w) {
+    if (!w) return fail(RS_E_INVALID, "rs_host_step_wait: null world");
+    if (!w->host_pending) return RS_OK;
+    ON_DEVICE(w, "rs_host_step_wait");
+    w->host_pending = false;
+    CUDA_TRY(cudaEventSynchronize(w->host_done));
+    return RS_OK;
 }
 
 }  // extern "C"

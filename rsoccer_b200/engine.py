@@ -238,3 +238,21 @@ class BatchedWorld:
             self.h, task, C.c_void_p(h_actions.data_ptr()), int(auto_reset), int(max_steps),
             C.c_void_p(h_obs.data_ptr()), C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_done.data_ptr()),
             C.c_void_p(h_trunc.data_ptr()), self._stream()), "rs_ssl_env_step_host")
+
+    # split-phase forms (rs_*_env_step_host_begin / rs_host_step_wait): enqueue on the current stream and
+    # return; host_step_wait() blocks until the outputs have landed.  The buffers belong to the library until then.
+    def vss_env_step_host_begin(self, h_actions, h_obs, h_rew, h_done, h_trunc, auto_reset=True, max_steps=1200):
+        _lib.check(self.L.rs_vss_env_step_host_begin(
+            self.h, C.c_void_p(h_actions.data_ptr()), int(auto_reset), int(max_steps),
+            C.c_void_p(h_obs.data_ptr()), C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_done.data_ptr()),
+            C.c_void_p(h_trunc.data_ptr()), self._stream()), "rs_vss_env_step_host_begin")
+
+    def ssl_env_step_host_begin(self, task, h_actions, h_obs, h_rew, h_done, h_trunc, auto_reset=True,
+                                max_steps=1000):
+        _lib.check(self.L.rs_ssl_env_step_host_begin(
+            self.h, task, C.c_void_p(h_actions.data_ptr()), int(auto_reset), int(max_steps),
+            C.c_void_p(h_obs.data_ptr()), C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_done.data_ptr()),
+            C.c_void_p(h_trunc.data_ptr()), self._stream()), "rs_ssl_env_step_host_begin")
+
+    def host_step_wait(self):
+        _lib.check(self.L.rs_host_step_wait(self.h), "rs_host_step_wait")

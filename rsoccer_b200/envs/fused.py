@@ -96,6 +96,22 @@ class _FusedVecEnv:
         self._step_host(a, o, r, d, t)
         return o.numpy(), r.numpy(), d.numpy().astype(bool), t.numpy().astype(bool)
 
+    # ---- the same, split-phase (gymnasium VectorEnv's step_async / step_wait): with two env groups on two CUDA
+    # streams one group's observations cross PCIe while the other group steps
+    def step_async(self, actions_np):
+        if self._pinned is None:
+            n = self.num_envs
+            self._pinned = (torch.empty(n, self.ACT_DIM, dtype=torch.float32).pin_memory(),
+                            ) + self.world.alloc_host_outputs(self.TASK)
+        a, o, r, d, t = self._pinned
+        a.copy_(torch.as_tensor(actions_np, dtype=torch.float32).reshape(a.shape))
+        self._step_host(a, o, r, d, t, begin=True)
+
+    def step_wait(self):
+        self.world.host_step_wait()
+        _, o, r, d, t = self._pinned
+        return o.numpy(), r.numpy(), d.numpy().astype(bool), t.numpy().astype(bool)
+
     def render(self, index=0, width_px=750):
         """RGB picture [H, W, 3] uint8 of match `index` (vss_gym_base.py:148-187, rgb_array mode)."""
         from ..render import render_rgb
@@ -120,8 +136,9 @@ class VSSVecEnv(_FusedVecEnv):
         return self.world.vss_env_step(actions, auto_reset=self.auto_reset, max_steps=self.max_episode_steps,
                                        out=self._out)
 
-    def _step_host(self, a, o, r, d, t):
-        self.world.vss_env_step_host(a, o, r, d, t, auto_reset=self.auto_reset, max_steps=self.max_episode_steps)
+    def _step_host(self, a, o, r, d, t, begin=False):
+        f = self.world.vss_env_step_host_begin if begin else self.world.vss_env_step_host
+        f(a, o, r, d, t, auto_reset=self.auto_reset, max_steps=self.max_episode_steps)
 
 
 class _SSLFused(_FusedVecEnv):
@@ -132,9 +149,9 @@ class _SSLFused(_FusedVecEnv):
         return self.world.ssl_env_step(self.TASK, actions, auto_reset=self.auto_reset,
                                        max_steps=self.max_episode_steps, out=self._out)
 
-    def _step_host(self, a, o, r, d, t):
-        self.world.ssl_env_step_host(self.TASK, a, o, r, d, t, auto_reset=self.auto_reset,
-                                     max_steps=self.max_episode_steps)
+    def _step_host(self, a, o, r, d, t, begin=False):
+        f = self.world.ssl_env_step_host_begin if begin else self.world.ssl_env_step_host
+        f(self.TASK, a, o, r, d, t, auto_reset=self.auto_reset, max_steps=self.max_episode_steps)
 
 
 class SSLStaticDefendersVecEnv(_SSLFused):

@@ -283,6 +283,84 @@ def test_host_step_equals_the_device_step_at_a_lane_per_match_size(engine):
     assert torch.equal(env.world.get_raw(), ref.world.get_raw()) and env.world.t == ref.world.t
 
 
+@pytest.mark.parametrize("task", ["vss", "sd", "cp"])
+def test_host_step_with_pinned_actions_in_place_or_copied(_engine_module, task):
+    """RS_OPT_HOST_COPY_ACTIONS: pinned host actions read in place over PCIe (0), staged with a copy (1) or chosen
+    by row size (-1, the default), and pageable actions (always copied) all give the device-tensor step's bits"""
+    E, L = _engine_module, _lib_consts()
+    kind, ft, nb, ny, tid, ad = {"vss": (0, 0, 3, 3, E.TASK_VSS_V0, 2), "sd": (1, 2, 1, 6, E.TASK_SSL_STATIC_DEFENDERS_V0, 5),
+                                 "cp": (1, 2, 1, 1, E.TASK_SSL_CONTESTED_POSSESSION_V0, 5)}[task]
+    n = 3001
+    g = torch.Generator().manual_seed(5)
+    acts = [torch.rand(n, ad, generator=g) * 2 - 1 for _ in range(6)]
+
+    def run(mode, pinned):
+        w = E.BatchedWorld(kind, ft, nb, ny, 25, n, seed=4)
+        w.task_reset(tid)
+        if mode is None:
+            outs = []
+            for a in acts:
+                o = w.vss_env_step(a.cuda()) if task == "vss" else w.ssl_env_step(tid, a.cuda())
+                outs.append([x.cpu().clone() for x in o])
+            return outs, w.get_raw().cpu()
+        assert w.get_option(L.OPT_HOST_COPY_ACTIONS) == -1
+        w.set_option(L.OPT_HOST_COPY_ACTIONS, mode)
+        h_out = w.alloc_host_outputs(tid)
+        h_act = torch.empty(n, ad).pin_memory() if pinned else torch.empty(n, ad)
+        outs = []
+        for a in acts:
+            h_act.copy_(a)
+            if task == "vss":
+                w.vss_env_step_host(h_act, *h_out)
+            else:
+                w.ssl_env_step_host(tid, h_act, *h_out)
+            outs.append([x.clone() for x in h_out])
+        return outs, w.get_raw().cpu()
+
+    ref_outs, ref_raw = run(None, False)
+    for mode, pinned in ((-1, True), (0, True), (1, True), (-1, False), (0, False)):
+        outs, raw = run(mode, pinned)
+        for step, (o, r) in enumerate(zip(outs, ref_outs)):
+            for x, y in zip(o, r):
+                assert torch.equal(x, y), (mode, pinned, step)
+        assert torch.equal(raw, ref_raw), (mode, pinned)
+    with pytest.raises(Exception):
+        E.BatchedWorld(kind, ft, nb, ny, 25, 8, seed=4).set_option(L.OPT_HOST_COPY_ACTIONS, 2)
+
+
+def test_split_phase_host_steps_of_two_env_groups(engine):
+    """step_async / step_wait (rs_*_env_step_host_begin + rs_host_step_wait): two env groups on two streams,
+    one stepping while the other's outputs cross PCIe, give the blocking step_host's bits; a second begin
+    while one is pending is refused."""
+    from rsoccer_b200 import envs
+    n = 4099
+    ga = [envs.make(name, num_envs=n, seed=11 + i) for i, name in enumerate(("VSS-v0", "SSLStaticDefenders-v0"))]
+    gb = [envs.make(name, num_envs=n, seed=11 + i) for i, name in enumerate(("VSS-v0", "SSLStaticDefenders-v0"))]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for e in ga + gb:
+        e.reset()
+    torch.cuda.synchronize()
+    g = torch.Generator().manual_seed(2)
+    acts = [[(torch.rand(n, e.ACT_DIM, generator=g) * 2 - 1).numpy() for e in ga] for _ in range(12)]
+    for i, e in enumerate(ga):                      # prologue: both groups in flight
+        with torch.cuda.stream(streams[i]):
+            e.step_async(acts[0][i])
+    with pytest.raises(Exception):
+        ga[0].step_async(acts[0][0])
+    for t in range(12):
+        for i, e in enumerate(ga):
+            got = [x.copy() for x in e.step_wait()]
+            if t + 1 < 12:
+                with torch.cuda.stream(streams[i]):
+                    e.step_async(acts[t + 1][i])    # group i steps again while the other group is consumed
+            want = gb[i].step_host(acts[t][i])
+            for x, y in zip(got, want):
+                assert np.array_equal(x, y), (t, i)
+    for a, b in zip(ga, gb):
+        a.world.host_step_wait()                    # nothing pending: a no-op
+        assert torch.equal(a.world.get_raw(), b.world.get_raw())
+
+
 def test_render_rgb_array_of_env_i_of_a_batch(engine):
     """env.render(index) with render_mode="rgb_array": the picture of ONE match of the batch, drawn from
     the device state (ball where get_state says it is); a window mode is not offered."""
