@@ -534,10 +534,13 @@ def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            p0 = torch.cuda.Event(enable_timing=True)
+            pe = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+            p0.record(gst[0])                                  # before anything of either group is enqueued
             run(e2e_steps)
+            pe[0].record(gst[0]); pe[1].record(gst[1])
             torch.cuda.synchronize()
-            ms_p = (time.perf_counter() - t0) * 1e3
+            ms_p = max(p0.elapsed_time(pe[0]), p0.elapsed_time(pe[1]))
             if world > 1:
                 t = torch.tensor([ms_p], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -547,8 +550,8 @@ def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_
             pipe = {"value": N * world * e2e_steps / (ms_p * 1e-3), "unit": UNIT, "steps": e2e_steps,
                     "ms_per_step": ms_p / e2e_steps, "frac_of_ceiling": ms_c / ms_p,
                     "what": "two env groups of %d matches on two streams through rs_*_env_step_host_begin / "
-                            "rs_host_step_wait: one group steps while the other's outputs cross PCIe; host wall "
-                            "clock around the loop (two streams), same bytes per step as the blocking call" % n2}
+                            "rs_host_step_wait: one group steps while the other's outputs cross PCIe; CUDA events, "
+                            "first enqueue to the later of the two streams' ends; same bytes per step as the blocking call" % n2}
         h2d = N * wl.act_dim * 4
         res["e2e"] = {
             "value": N * world * e2e_steps / (ms_e * 1e-3), "unit": UNIT, "steps": e2e_steps,
