@@ -268,6 +268,13 @@ def run_reference(args, rank, out):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not have_robosim:
+        # the bare C loop on ONE thread next to the all-threads figure
+        try:
+            one = cpu_baseline_run(cfg["task"], 1, 1.5, envs=4096)
+            line["single_thread"] = {"value": one["value"], "unit": UNIT, "cores": one["cores"], "kind": "port", "sample": one["sample"]}
+        except Exception as e:
+            line["single_thread"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     wrapped = reference_vssenv_run(3.0) if cfg["task"] == "vss" and not have_robosim else None
     if wrapped is not None:
         line["reference_vssenv"] = wrapped
