@@ -45,6 +45,7 @@ def run(argv):
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--worlds", type=int, default=8, help="1 = state stays L2 resident")
     ap.add_argument("--env", default="", help="extra environment for the children, K=V,K=V")
+    ap.add_argument("--graph-steps", type=int, default=8, help="steps per captured graph (step overlap drains at every replay)")
     a = ap.parse_args(argv)
     import torch  # noqa: F401  (imported before the fork: children pay only CUDA init)
     libs = sorted(f for f in os.listdir(VDIR) if f.endswith(".so"))
@@ -65,7 +66,7 @@ def run(argv):
             res = []
             for n in [int(x) for x in a.sizes.split(",")]:
                 try:
-                    res.append("%d:%.2f" % (n, T.time_steps(a.task, n, n_worlds=a.worlds, steps=a.steps, graph_steps=8)))
+                    res.append("%d:%.2f" % (n, T.time_steps(a.task, n, n_worlds=a.worlds, steps=a.steps, graph_steps=a.graph_steps)))
                 except Exception as ex:  # noqa: BLE001
                     res.append("%d:ERR(%s)" % (n, str(ex)[:80]))
             line = "%-28s task=%s mode=%s worlds=%d %s  %s" % (f[4:-3], a.task, a.mode, a.worlds, a.env, "  ".join(res))
