@@ -387,12 +387,25 @@ class Workload:
             w.set_option(_lib.OPT_STEP_OVERLAP, mode)
         self.overlap = mode
 
-    def capture(self, stream):
+    def capture(self, stream, n_streams=1):
+        """One CUDA graph of G steps.  n_streams > 1: the worlds are spread over that many side streams, so the
+        chains of different worlds are PARALLEL branches of the graph (each world's own steps stay a chain on its
+        stream) -- how independent small worlds are driven when launch latency, not the GPU, is the limit."""
         torch = self.torch
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=stream):
-            for i in range(self.G):
-                self.step(i)
+            if n_streams <= 1:
+                for i in range(self.G):
+                    self.step(i)
+            else:
+                side = [torch.cuda.Stream(device=self.dev) for _ in range(n_streams)]
+                for sd in side:
+                    sd.wait_stream(stream)
+                for i in range(self.G):
+                    with torch.cuda.stream(side[(i % self.M) % n_streams]):
+                        self.step(i)
+                for sd in side:
+                    stream.wait_stream(sd)
         return g, self.G
 
     def host_step(self, bufs):
@@ -408,7 +421,8 @@ class Workload:
         self.worlds = []
 
 
-def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_steps=50, clock_index=None, pipelined=False):
+def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_steps=50, clock_index=None, pipelined=False,
+            n_streams=1):
     """settle -> capture -> W warm-up launches -> timed graph replays; then the e2e loop."""
     res = {}
     with torch.cuda.stream(stream):
@@ -416,7 +430,7 @@ def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_
             for i in range(wl.cfg["settle"] * wl.M):
                 wl.step(i)
         stream.synchronize()
-        graph, G = wl.capture(stream)
+        graph, G = wl.capture(stream, n_streams)
         graph.replay()
         for i in range(W):
             wl.step(i)
@@ -729,6 +743,26 @@ def main():
             w2 = Workload(torch, E, name, c, c["envs"], dev, rank, args.overlap, K, seed_base=1 + names.index(name))
             r2 = measure(torch, dist, w2, K, W, args.min_ms / 2, stream, world, dev, e2e_steps=30)
             subs[name] = summarise(w2, r2, K, W, world, peak, peak_src)
+            if c["envs"] <= 16384:
+                # small worlds are bound by launch latency, not by the GPU; two more regimes for the record:
+                # (1) the worlds of the rotation as PARALLEL branches of the graph (16 streams);
+                rp = measure(torch, dist, w2, K, W, args.min_ms / 2, stream, world, dev, settle=False, e2e_steps=0, n_streams=16)
+                subs[name]["parallel_streams"] = {
+                    "streams": 16, "ms_per_step": rp["ms_per_step"], "value": c["envs"] * world / (rp["ms_per_step"] * 1e-3),
+                    "frac": c["alg"] * c["envs"] / (rp["ms_per_step"] * 1e-3) / 1e9 / peak,
+                    "what": "the same worlds captured on 16 streams: the chains of different worlds are parallel branches "
+                            "of the graph instead of one chain of programmatic launches"}
+                w2.close()
+                del w2
+                # (2) ONE world stepped again and again: what a user of exactly this config sees per step
+                w2 = Workload(torch, E, name, c, c["envs"], dev, rank, 2, K, seed_base=11 + names.index(name), worlds=1)
+                rc1 = measure(torch, dist, w2, K, W, args.min_ms / 4, stream, world, dev, e2e_steps=0)
+                w2.set_overlap(0)
+                rs1 = measure(torch, dist, w2, K, W, args.min_ms / 4, stream, world, dev, settle=False, e2e_steps=0)
+                subs[name]["single_world"] = {
+                    "overlap2_ms_per_step": rc1["ms_per_step"], "serialized_ms_per_step": rs1["ms_per_step"],
+                    "serialized_value": c["envs"] * world / (rs1["ms_per_step"] * 1e-3),
+                    "what": "one world of this size stepped back to back (a dependency chain; launch / latency bound)"}
             w2.close()
             del w2
             torch.cuda.empty_cache()

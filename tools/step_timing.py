@@ -35,7 +35,7 @@ TASKS = {
 }
 
 
-def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=True, graph_steps=0):
+def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=True, graph_steps=0, n_streams=1):
     """us per launch of one fused step of `task_name` at `envs` matches (see module docstring)."""
     kind, ft, nb, ny, task, adim = TASKS[task_name]
     dev = torch.device("cuda", 0)
@@ -79,8 +79,20 @@ def time_steps(task_name, envs, n_worlds=8, steps=4000, warmup=300, use_graph=Tr
         if use_graph:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
-                for i in range(M):
-                    step(i)
+                if n_streams <= 1:
+                    for i in range(M):
+                        step(i)
+                else:
+                    # one stream per group of worlds: the chains of different worlds are parallel branches of the
+                    # graph, each world's own steps stay a chain (programmatic edges) on its stream
+                    side = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+                    for sd in side:
+                        sd.wait_stream(stream)
+                    for i in range(M):
+                        with torch.cuda.stream(side[(i % n_worlds) % n_streams]):
+                            step(i)
+                    for sd in side:
+                        stream.wait_stream(sd)
             graph.replay()
             stream.synchronize()
         reps = max(1, steps // M)
@@ -109,8 +121,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=300, help="untimed steps per world")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--graph-steps", type=int, default=0, help="steps per captured graph (default: one pass over the worlds)")
+    ap.add_argument("--streams", type=int, default=1, help="capture the worlds on this many streams (parallel branches of the graph)")
     a = ap.parse_args()
-    us = time_steps(a.task, a.envs, a.worlds, a.steps, a.warmup, not a.no_graph, a.graph_steps)
+    us = time_steps(a.task, a.envs, a.worlds, a.steps, a.warmup, not a.no_graph, a.graph_steps, a.streams)
     mode = "per_match" if os.environ.get("RS_PER_MATCH", "") == "1" else ("per_body" if os.environ.get("RS_PER_MATCH", "") == "0" else "auto")
     print("TIMING task=%s envs=%d mode=%s pdl=%s graph=%d  %.2f us/step  %.1f Menv-steps/s" % (
         a.task, a.envs, mode, os.environ.get("RS_PDL", "1"), not a.no_graph, us, a.envs / us))
