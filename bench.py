@@ -592,6 +592,30 @@ def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_
     return res
 
 
+def small_world_regimes(torch, dist, E, wl, rec, name, c, envs, K, W, args, stream, world, dev, rank, peak, seed_base):
+    """Small worlds are bound by launch latency, not by the GPU; two more regimes for the record (wl is closed,
+    the single-world workload is returned for the caller to close):
+    (1) the worlds of the rotation as PARALLEL branches of the graph (16 streams);
+    (2) ONE world stepped again and again: what a user of exactly this config sees per step."""
+    rp = measure(torch, dist, wl, K, W, args.min_ms / 2, stream, world, dev, settle=False, e2e_steps=0, n_streams=16)
+    rec["parallel_streams"] = {
+        "streams": 16, "ms_per_step": rp["ms_per_step"], "value": envs * world / (rp["ms_per_step"] * 1e-3),
+        "frac": c["alg"] * envs / (rp["ms_per_step"] * 1e-3) / 1e9 / peak,
+        "what": "the same worlds captured on 16 streams: the chains of different worlds are parallel branches "
+                "of the graph instead of one chain of programmatic launches"}
+    wl.close()
+    w1 = Workload(torch, E, name, c, envs, dev, rank, 2, K, seed_base=seed_base, worlds=1)
+    rc1 = measure(torch, dist, w1, K, W, args.min_ms / 4, stream, world, dev, e2e_steps=0)
+    w1.set_overlap(0)
+    rs1 = measure(torch, dist, w1, K, W, args.min_ms / 4, stream, world, dev, settle=False, e2e_steps=0)
+    rec["single_world"] = {
+        "overlap2_ms_per_step": rc1["ms_per_step"], "serialized_ms_per_step": rs1["ms_per_step"],
+        "overlap2_value": envs * world / (rc1["ms_per_step"] * 1e-3),
+        "serialized_value": envs * world / (rs1["ms_per_step"] * 1e-3),
+        "what": "one world of this size per GPU stepped back to back (a dependency chain; launch / latency bound)"}
+    return w1
+
+
 def summarise(wl, res, K, W, world, peak, peak_src):
     per_launch_s = res["ms_per_step"] * 1e-3
     achieved = wl.cfg["alg"] * wl.N / per_launch_s / 1e9
@@ -744,25 +768,8 @@ def main():
             r2 = measure(torch, dist, w2, K, W, args.min_ms / 2, stream, world, dev, e2e_steps=30)
             subs[name] = summarise(w2, r2, K, W, world, peak, peak_src)
             if c["envs"] <= 16384:
-                # small worlds are bound by launch latency, not by the GPU; two more regimes for the record:
-                # (1) the worlds of the rotation as PARALLEL branches of the graph (16 streams);
-                rp = measure(torch, dist, w2, K, W, args.min_ms / 2, stream, world, dev, settle=False, e2e_steps=0, n_streams=16)
-                subs[name]["parallel_streams"] = {
-                    "streams": 16, "ms_per_step": rp["ms_per_step"], "value": c["envs"] * world / (rp["ms_per_step"] * 1e-3),
-                    "frac": c["alg"] * c["envs"] / (rp["ms_per_step"] * 1e-3) / 1e9 / peak,
-                    "what": "the same worlds captured on 16 streams: the chains of different worlds are parallel branches "
-                            "of the graph instead of one chain of programmatic launches"}
-                w2.close()
-                del w2
-                # (2) ONE world stepped again and again: what a user of exactly this config sees per step
-                w2 = Workload(torch, E, name, c, c["envs"], dev, rank, 2, K, seed_base=11 + names.index(name), worlds=1)
-                rc1 = measure(torch, dist, w2, K, W, args.min_ms / 4, stream, world, dev, e2e_steps=0)
-                w2.set_overlap(0)
-                rs1 = measure(torch, dist, w2, K, W, args.min_ms / 4, stream, world, dev, settle=False, e2e_steps=0)
-                subs[name]["single_world"] = {
-                    "overlap2_ms_per_step": rc1["ms_per_step"], "serialized_ms_per_step": rs1["ms_per_step"],
-                    "serialized_value": c["envs"] * world / (rs1["ms_per_step"] * 1e-3),
-                    "what": "one world of this size stepped back to back (a dependency chain; launch / latency bound)"}
+                w2 = small_world_regimes(torch, dist, E, w2, subs[name], name, c, c["envs"], K, W, args, stream, world, dev, rank,
+                                         peak, 11 + names.index(name))
             w2.close()
             del w2
             torch.cuda.empty_cache()
@@ -775,6 +782,9 @@ def main():
             extras["strong"] = summarise(w3, r3, K, W, world, peak, peak_src)
             extras["strong"]["scaling"] = "strong"
             extras["strong"]["envs_total"] = n_s * world
+            if n_s <= 16384:
+                w3 = small_world_regimes(torch, dist, E, w3, extras["strong"], "vss65536_strong", c, n_s, K, W, args, stream, world,
+                                         dev, rank, peak, 15)
             w3.close()
             del w3
 
