@@ -186,3 +186,41 @@ def test_render_rgb_array_of_one_match(oracle, kind):
         assert px == (RR.BLUE if k < nb else RR.YELLOW), (k, px)
     with pytest.raises(ValueError):
         RR.render_rgb(st[:-1], field, kind, nb, ny)
+
+
+def test_committed_bench_lines_keep_the_driver_contract():
+    """the JSON lines bench.py printed on the B200 (profiles/r2_bench_line*.json) carry every key the driver and the
+    tier's measurement section name, with consistent values"""
+    import json
+    prof = os.path.join(ROOT, "profiles")
+    line = json.load(open(os.path.join(prof, "r2_bench_line.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    e = line["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
+    assert e["h2d_bytes_per_step"] == 65536 * 2 * 4 and e["d2h_bytes_per_step"] == 65536 * (40 * 4 + 4 + 1 + 1)
+    assert 0 < e["value"] < line["value"]                     # host copies inside the timed region: never the device figure
+    r = line["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    # achieved = 592 algorithmic bytes x 65 536 matches / measured launch time
+    assert abs(r["achieved"] - 592 * 65536 / (line["ms_per_step"] * 1e-3) / 1e9) < 1e-3 * r["achieved"]
+    assert abs(line["value"] - 65536 / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"]
+    c = line["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference")
+    assert line["gpu_launches"] > 0
+    for name in ("vss4096", "sd4096", "cp16384", "vss262144_sharded"):
+        assert {"ms_per_step", "roofline", "e2e"} <= set(line["configs"][name]), name
+    assert line["strong"]["scaling"] == "strong" and line["strong"]["envs_total"] == 65536
+    ref = json.load(open(os.path.join(prof, "r2_bench_line_reference.json")))
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["cpu_baseline"]["value"] == ref["value"] == ref["e2e"]["value"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
+    for n in (2, 4, 8):
+        ln = json.load(open(os.path.join(prof, "r2_bench_line_n%d.json" % n)))
+        assert ln["n_gpus"] == n and ln["scaling"] == "weak" and ln["config"]["envs_per_gpu"] == 65536
+        assert abs(ln["value"] - n * 65536 / (ln["ms_per_step"] * 1e-3)) < 1e-6 * ln["value"]
