@@ -83,7 +83,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.times, self.proc = index, [], [], None
 
     def start(self):
         try:
@@ -98,9 +98,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
+            self.times.append(time.perf_counter())
             self.rows.append(line.strip())
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """statistics of the samples taken in [t_from, t_to] (perf_counter; default: all of them)"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.1)
@@ -111,6 +113,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if t_from is not None:
+            # a sample is printed up to one period (20 ms) after it was taken
+            keep = [r for t, r in zip(self.times, self.rows) if t_from <= t <= (t_to if t_to is not None else 1e30) + 0.03]
+            if len(keep) >= 2:
+                self.rows = keep
         for r in self.rows:
             c = [x.strip() for x in r.split(",")]
             if len(c) < 7:
@@ -433,6 +440,10 @@ def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_
             n_streams=1):
     """settle -> capture -> W warm-up launches -> timed graph replays; then the e2e loop."""
     res = {}
+    sampler = None
+    if clock_index is not None:
+        sampler = ClockSampler(clock_index)      # started here, long before the timed region: no idle pause in front of it
+        sampler.start()
     with torch.cuda.stream(stream):
         if settle:
             for i in range(wl.cfg["settle"] * wl.M):
@@ -452,26 +463,23 @@ def measure(torch, dist, wl, K, W, min_ms, stream, world, dev, settle=True, e2e_
         t = torch.tensor([replays], device=dev, dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         replays = int(t.item())
-    sampler = None
-    if clock_index is not None:
-        sampler = ClockSampler(clock_index)
-        sampler.start()
-        time.sleep(0.25)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_from = time.perf_counter()
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(replays):
             graph.replay()
         ev1.record(stream)
     torch.cuda.synchronize()
+    t_to = time.perf_counter()
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
     if sampler is not None:
-        res["clocks"] = sampler.stop()
+        res["clocks"] = sampler.stop(t_from, t_to)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
