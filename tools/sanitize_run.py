@@ -2,7 +2,8 @@
 """Small driver for compute-sanitizer (memcheck / racecheck / initcheck): every fused task step,
 both kernel mappings, ragged sizes, short episodes so that the auto-reset paths run, crowded scenes so that
 the shared-memory contact resolve runs, and every step-overlap mode with back-to-back launches on a fixed
-action buffer so that the tile hand-over runs.
+action buffer so that the tile hand-over runs; the host-buffer steps (blocking and split-phase, actions in place /
+staged / pageable).
 
   compute-sanitizer --tool racecheck python tools/sanitize_run.py
 """
@@ -44,6 +45,20 @@ for mode, packed, overlap in (("1", "1", 0), ("1", "0", 0), ("0", "0", 0), ("1",
                     else:
                         w.ssl_env_step(task, a, max_steps=3, out=out)
             assert w.get_option(_lib.OPT_OVERLAP_ERRORS) == 0
+            # host-buffer steps: blocking (pinned actions in place / staged, pageable), then split-phase
+            h_out = w.alloc_host_outputs(task)
+            for pinned, copy_act in ((True, -1), (True, 1 if task else 0), (False, -1)):
+                w.set_option(_lib.OPT_HOST_COPY_ACTIONS, copy_act)
+                h_act = torch.rand(n, nact, generator=g) * 2 - 1
+                if pinned:
+                    h_act = h_act.pin_memory()
+                if task == 0:
+                    w.vss_env_step_host(h_act, *h_out, max_steps=3)
+                    w.vss_env_step_host_begin(h_act, *h_out, max_steps=3)
+                else:
+                    w.ssl_env_step_host(task, h_act, *h_out, max_steps=3)
+                    w.ssl_env_step_host_begin(task, h_act, *h_out, max_steps=3)
+                w.host_step_wait()
             c = torch.rand(n, nb + ny, w.cmd_dim, generator=g).cuda()
             w.step(c)
             w.get_state()
