@@ -14,6 +14,12 @@ per key (zero-copy views of the on-device accumulators).  When an episode ends t
 observation is the first one of the next episode; `truncated` follows the registered step
 limits (rsoccer_gym/__init__.py:3-30).
 
+Terminal observations: construct the env with `final_obs=True` and `info["final_obs"]` holds every env's observation
+BEFORE any reset of this step (the terminal observation of the envs flagged in `info["_final_obs"]` = terminated |
+truncated: what a time-limit bootstrap needs, gymnasium's same-step autoreset convention).  That mode steps without
+the in-kernel reset and re-places the ended matches with one masked `rs_task_reset` launch (three launches per
+step instead of one; placements then come from the reset stream of the Philox generator instead of the auto-reset one).
+
 Aliasing: `step` / `reset` return the SAME preallocated tensors on every call (zero-copy: the
 kernel writes them in place).  A rollout buffer must copy what it keeps (`buf[t].copy_(obs)`),
 or construct the env with `copy_outputs=True` to get fresh tensors from every call.
@@ -40,7 +46,7 @@ class _FusedVecEnv:
     NORM_BOUNDS = 1.2
 
     def __init__(self, num_envs=1, device=None, seed=0, env_offset=0, auto_reset=True, max_episode_steps=None,
-                 field_type=None, render_mode=None, copy_outputs=False):
+                 field_type=None, render_mode=None, copy_outputs=False, final_obs=False):
         if render_mode not in (None, "rgb_array"):
             raise NotImplementedError("render_mode %r: only 'rgb_array' (no window) is offered" % (render_mode,))
         self.render_mode = render_mode
@@ -58,6 +64,8 @@ class _FusedVecEnv:
         self.observation_space = BoxSpec(-self.NORM_BOUNDS, self.NORM_BOUNDS, (self.num_envs, self.obs_dim))
         self._out = self.world.alloc_outputs(self.TASK)
         self.copy_outputs = bool(copy_outputs)
+        self.final_obs = bool(final_obs)
+        self._final = torch.empty_like(self._out[0]) if self.final_obs else None
         self._pinned = None
         self.field = None
 
@@ -69,10 +77,25 @@ class _FusedVecEnv:
         return (obs.clone() if self.copy_outputs else obs), self.info()
 
     def step(self, actions):
+        if self.final_obs and self.auto_reset:
+            return self._step_with_final_obs(actions)
         obs, rew, done, trunc = self._step(actions)
         if self.copy_outputs:
             obs, rew = obs.clone(), rew.clone()
         return obs, rew, done.bool(), trunc.bool(), self.info()
+
+    def _step_with_final_obs(self, actions):
+        # the fused step without its in-kernel reset: the observation rows of ended matches are terminal observations
+        obs, rew, done, trunc = self._step(actions, auto_reset=False)
+        ended = done | trunc
+        self._final.copy_(obs)
+        self.world.task_reset(self.TASK, mask=ended, obs=obs)      # rewrites the rows (and the state) of the ended matches only
+        info = self.info()
+        info["final_obs"] = self._final.clone() if self.copy_outputs else self._final
+        info["_final_obs"] = ended.bool()
+        if self.copy_outputs:
+            obs, rew = obs.clone(), rew.clone()
+        return obs, rew, done.bool(), trunc.bool(), info
 
     def step_raw(self, actions):
         """step without building the info dict / bool casts: (obs, reward, done u8, trunc u8)"""
@@ -132,9 +155,9 @@ class VSSVecEnv(_FusedVecEnv):
     MAX_EPISODE_STEPS = 1200              # rsoccer_gym/__init__.py:4
     INFO_KEYS = VSS_INFO_KEYS
 
-    def _step(self, actions):
-        return self.world.vss_env_step(actions, auto_reset=self.auto_reset, max_steps=self.max_episode_steps,
-                                       out=self._out)
+    def _step(self, actions, auto_reset=None):
+        return self.world.vss_env_step(actions, auto_reset=self.auto_reset if auto_reset is None else auto_reset,
+                                       max_steps=self.max_episode_steps, out=self._out)
 
     def _step_host(self, a, o, r, d, t, begin=False):
         f = self.world.vss_env_step_host_begin if begin else self.world.vss_env_step_host
@@ -145,8 +168,8 @@ class _SSLFused(_FusedVecEnv):
     KIND, FIELD_TYPE, ACT_DIM = _E.KIND_SSL, 2, 5
     INFO_KEYS = SSL_INFO_KEYS
 
-    def _step(self, actions):
-        return self.world.ssl_env_step(self.TASK, actions, auto_reset=self.auto_reset,
+    def _step(self, actions, auto_reset=None):
+        return self.world.ssl_env_step(self.TASK, actions, auto_reset=self.auto_reset if auto_reset is None else auto_reset,
                                        max_steps=self.max_episode_steps, out=self._out)
 
     def _step_host(self, a, o, r, d, t, begin=False):

@@ -361,6 +361,43 @@ def test_split_phase_host_steps_of_two_env_groups(engine):
         assert torch.equal(a.world.get_raw(), b.world.get_raw())
 
 
+@pytest.mark.parametrize("env_id", ["VSS-v0", "SSLStaticDefenders-v0", "SSLContestedPossession-v0"])
+def test_final_obs_mode_exposes_the_terminal_observation(engine, env_id):
+    """final_obs=True: info["final_obs"] is the observation of the step BEFORE any reset (rows flagged in
+    info["_final_obs"] = terminated | truncated are terminal observations), obs holds the first observation of the
+    next episode for those rows; everything else equals the same env stepped without auto-reset."""
+    from rsoccer_b200 import envs
+    n, horizon = 700, 5
+    a_env = envs.make(env_id, num_envs=n, seed=21, max_episode_steps=horizon, final_obs=True)
+    b_env = envs.make(env_id, num_envs=n, seed=21, max_episode_steps=horizon, auto_reset=False)
+    o0, _ = a_env.reset()
+    o1, _ = b_env.reset()
+    assert torch.equal(o0, o1)
+    g = torch.Generator().manual_seed(9)
+    ended_total = 0
+    for t in range(horizon):                      # no env of `b_env` is ever reset, so the two agree until the first end
+        act = (torch.rand(n, a_env.ACT_DIM, generator=g) * 2 - 1).cuda()
+        oa, ra, da, ta, info = a_env.step(act)
+        ob, rb, db, tb, _ = b_env.step(act)
+        first = t == 0 or ended_total == 0
+        ended = info["_final_obs"]
+        assert torch.equal(ended, da | ta)
+        if first:
+            assert torch.equal(info["final_obs"], ob) and torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(ta, tb)
+            keep = ~ended
+            assert torch.equal(oa[keep], ob[keep])          # rows that did not end: the ordinary observation
+            if ended.any():
+                assert not torch.equal(oa[ended], ob[ended])  # ended rows: first observation of the next episode
+                assert int(a_env.world.steps[:n][ended].max()) == 0
+        ended_total += int(ended.sum())
+        if not first:
+            break
+    assert ended_total > 0                        # the TimeLimit at the latest ends every env within the horizon
+    # after the truncation step every row of `a_env` has been re-placed and steps on
+    oa, ra, da, ta, info = a_env.step((torch.rand(n, a_env.ACT_DIM, generator=g) * 2 - 1).cuda())
+    assert torch.isfinite(oa).all() and int(a_env.world.steps[:n].max()) <= horizon
+
+
 def test_render_rgb_array_of_env_i_of_a_batch(engine):
     """env.render(index) with render_mode="rgb_array": the picture of ONE match of the batch, drawn from
     the device state (ball where get_state says it is); a window mode is not offered."""
