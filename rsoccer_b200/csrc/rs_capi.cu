@@ -56,10 +56,13 @@ struct VssStepArgs {
 // DENSE: the same source compiled for 11 resident CTAs per SM (80 registers instead of 114, no spills, same
 // instruction count).  When several worlds are stepped round-robin on one stream (RS_OPT_STEP_OVERLAP = 3)
 // consecutive launches are independent and as many CTAs of the NEXT step as registers allow should be
-// resident (65 536 matches, 8 worlds: 10.7 -> 9.2 us per step).  A launch that starts on an empty GPU, or
-// behind a true dependency (one world stepped again and again), wants its 1 024 CTAs spread over all 148
-// SMs, 7 per SM -- with DENSE the block scheduler packs them 11 per SM onto 93 SMs (15.8 -> 19.5 us
-// serialised, 12.8 -> 16.6 us chained on one world), so the caller chooses.
+// resident (65 536 matches, 8 worlds: 10.7 -> 9.2 us per step).  A launch behind a true dependency (every step
+// waits for the previous grid, or one world stepped again and again) wants its 1 024 CTAs spread evenly, 7 per
+// SM.  With DENSE and programmatic launches up to 5 CTAs per SM of the NEXT step become resident early and
+// wait; the ~280 that did not fit then land, it seems, on whichever SMs finish first, 7 at a time, so that a
+// few SMs run 12 CTAs of the step and the others 5 (15.8 -> 19.5 us serialised, 12.8 -> 16.6 us chained on one world; with
+// RS_PDL=0 the dense build runs 15.6 us and alone under ncu all 148 SMs are busy, profiles/r2_logs/
+// dense_pdl.log), so the caller chooses.
 template <int NB, int NY, int BS, int F0 /* 0: run-time physics constants.  1: VssF0's, immediates instead of
           constant-bank loads.  2: VssF0P, the same with the packed fp32x2 instruction forms (rs_device.cuh) */,
           bool DENSE = false>
@@ -1814,8 +1817,8 @@ static int vss_env_step_host(rs_world *w, const float *h_actions, int auto_reset
     const float *d_act = host_actions_on_device(w, h_actions, sizeof(float) * (size_t)w->n * RS_VSS_ACT, st);
     if (!d_act) return RS_E_CUDA;
     // a host step ends with a synchronize: its launch starts on an idle GPU and gains nothing from the tile protocol,
-    // so it is launched as if RS_OPT_STEP_OVERLAP were 0 (mode 3 would pick the dense build, which packs the grid onto
-    // 93 of the 148 SMs, and the lane-per-match kernels for small worlds)
+    // so it is launched as if RS_OPT_STEP_OVERLAP were 0 (mode 3 would pick the dense build, 80 registers for nothing
+    // here, and the lane-per-match kernels for small worlds)
     const int ov = w->overlap;
     w->overlap = 0;
     rc = rs_vss_env_step(w, d_act, nullptr, auto_reset, max_steps, w->s_obs, w->s_reward, w->s_done, w->s_trunc, nullptr, stream);
