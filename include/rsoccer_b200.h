@@ -235,7 +235,8 @@ int rs_debug_empty_step(rs_world *w, int chain, void *stream);
  *   bit 0  task kernels run one lane per BODY (else one lane per MATCH)
  *   bit 1  rs_step runs one lane per BODY
  *   bit 2  physics constants are compile-time immediates (VSS, field_type 0, 25 ms)
- *   bit 3  the VSS-v0 task kernel uses the packed fp32x2 instruction forms (large worlds; same results) */
+ *   bit 3  the VSS-v0 task kernel uses the packed fp32x2 instruction forms (worlds of >= 20 480 matches, and every
+ *          size under RS_OPT_STEP_OVERLAP = 3; same results) */
 int rs_kernel_flags(const rs_world *w);
 
 #ifdef __cplusplus

@@ -1218,6 +1218,9 @@ static bool use_lane_per_body(const rs_world *w, bool task_kernel) {
 #endif
 static bool use_packed(const rs_world *w) {
     if (w->packed >= 0) return w->packed != 0;
+    // RS_OPT_STEP_OVERLAP = 3 is the throughput regime whatever the world size (several worlds fill the GPU together:
+    // issue slots decide), and only the packed kernel has the dense build
+    if (w->overlap == 3) return true;
     return w->n >= RS_PACKED_MIN_MATCHES;
 }
 

@@ -256,7 +256,13 @@ def test_packed_and_scalar_instruction_forms_agree_bit_for_bit(engine, monkeypat
     assert (q.kernel_flags & 12) == 4
     monkeypatch.delenv("RS_PACKED")
     assert (E.BatchedWorld(0, 0, 3, 3, 25, 65536, seed=5).kernel_flags & 8)
-    assert not (E.BatchedWorld(0, 0, 3, 3, 25, 8192, seed=5).kernel_flags & 8)
+    # by world size -- except under RS_OPT_STEP_OVERLAP = 3, the throughput regime, which takes the packed forms at every size
+    small = E.BatchedWorld(0, 0, 3, 3, 25, 8192, seed=5)
+    assert bool(small.kernel_flags & 8) == (small.get_option(_lib_consts().OPT_STEP_OVERLAP) == 3)
+    small.set_option(_lib_consts().OPT_STEP_OVERLAP, 0)
+    assert not (small.kernel_flags & 8)
+    small.set_option(_lib_consts().OPT_STEP_OVERLAP, 3)
+    assert small.kernel_flags & 8
     p.task_reset(E.TASK_VSS_V0); q.task_reset(E.TASK_VSS_V0)
     for _ in range(60):
         op = p.vss_env_step(a, max_steps=25)
